@@ -1,0 +1,201 @@
+/* yoloret_b200 C-ABI  -  the drop-in boundary of the B200 YOLO-ReT hot path.
+ *
+ * The reference (prakharg24/yoloret) is pure Python on TensorFlow and has no
+ * FFI of its own; its hot path runs inside TF ops.  This header
+ * is the seam the replacement creates: the Python host that mirrors the
+ * reference call surface (yoloret_b200/yolo.py, yoloret_b200/yolo3/model.py)
+ * binds these entry points with ctypes.  Each entry point cites the reference
+ * code whose TF ops it replaces.
+ *
+ * Conventions
+ *  - plain C: raw DEVICE pointers + sizes, no torch types; the caller owns all
+ *    memory including workspaces; nothing here allocates or synchronises.
+ *  - every call is stream-ordered on `stream` (a cudaStream_t passed as void*)
+ *    and may be captured into a CUDA graph.
+ *  - returns 0 on success, a negative yr_status otherwise; yr_last_error()
+ *    returns a thread-local message for the last failure.
+ *  - activations are NHWC fp32.  Every channel dimension is padded to a
+ *    multiple of 8 ("Cp") and the pad channels hold exact zeros; `ld` is the
+ *    element stride between consecutive pixels of a buffer (>= Cp), which lets
+ *    a producer write straight into a channel slice of a concat buffer
+ *    (Concatenate layers of reference code/yolo3/model.py:164-166,255,275,308,321
+ *    are never materialised by a copy).
+ */
+#ifndef YOLORET_B200_H_
+#define YOLORET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum yr_status {
+    YR_OK = 0,
+    YR_ERR_INVALID = -1,   /* bad argument (shape, alignment, null pointer) */
+    YR_ERR_UNSUPPORTED = -2,
+    YR_ERR_CUDA = -3,      /* a CUDA runtime call / launch failed */
+    YR_ERR_WORKSPACE = -4  /* caller-provided workspace too small */
+} yr_status;
+
+typedef enum yr_act { YR_ACT_NONE = 0, YR_ACT_RELU6 = 1, YR_ACT_SWISH = 2 } yr_act;
+
+typedef enum yr_op_kind {
+    YR_OP_STEM = 0,      /* dense 3x3 stride-2 conv, Cin=3 (+folded BN +act) */
+    YR_OP_PW = 1,        /* 1x1 conv = GEMM (+folded BN/bias +act +residual +SE scale) */
+    YR_OP_DW = 2,        /* depthwise kxk conv, k in {3,5}, stride in {1,2} (+folded BN +act) */
+    YR_OP_RESAMPLE = 3,  /* nearest x2 up-sampling / 2x2 / 4x4 max-pooling into a channel slice */
+    YR_OP_RFCR = 4,      /* fused RFCR fusion: 4x 1x1 conv + resize + weighted sum */
+    YR_OP_SE = 5         /* squeeze-excite gate: global mean -> FC -> swish -> FC -> sigmoid */
+} yr_op_kind;
+
+typedef enum yr_resample_mode { YR_UP2 = 0, YR_POOL2 = 1, YR_POOL4 = 2 } yr_resample_mode;
+
+/* One network layer.  A plan is an array of these executed in order by
+ * yr_run_ops().  Fields not used by a kind are ignored.
+ *
+ *  STEM     in  [B,H,W,3] (u8 if in_is_u8 else f32; u8 is scaled by 1/255 as
+ *               tf.io.decode_image(dtype=float32) does, reference code/yolo.py:106)
+ *           w   [3*3*3][Cp_out] (kh,kw,cin major; BN scale folded), bias [Cp_out]
+ *           out [B,Ho,Wo,ld_out]; TF 'SAME' padding (pad_t/pad_l = leading pad).
+ *           replaces Conv1+bn_Conv1+ReLU6 of tf.keras.applications.MobileNetV2
+ *           (reference code/yolo3/override.py:339) and the EfficientNet stem
+ *           (code/yolo3/efficientnet.py:636-645).
+ *  PW       in  [B*H*W rows][ld_in], C = K (multiple of 8)
+ *           w   [K][N] row-major (N multiple of 8, BN scale folded), bias [N]
+ *           res optional [rows][ld_res] added AFTER the activation-less BN
+ *               (MobileNetV2 block_N_add / MBConv id_skip, efficientnet.py:527-533)
+ *           scale optional [B][K]: SE gate multiplied into the A operand
+ *               (Multiply layer of SEBlock, efficientnet.py:435)
+ *           out [rows][ld_out].  Replaces every Conv2D(kernel_size=1) of
+ *           reference code/yolo3/model.py:98-114,152-155,243-247,263-267,299-318
+ *           and efficientnet.py:485-491,517-522.
+ *  DW       in [B,H,W,ld_in] C channels; w [k*k][C] (BN folded), bias [C];
+ *           out [B,Ho,Wo,ld_out].  DepthwiseConv2D of MobileNetV2 blocks,
+ *           efficientnet.py:501-506 and model.py:20-23.
+ *  RESAMPLE in [B,H,W,ld_in] C channels -> out [B,Ho,Wo,ld_out] (mode):
+ *           UpSampling2D / MaxPooling2D of model.py:139-144,157,164-166,254,274,307,320.
+ *  RFCR     in=b1 [B,H/2,W/2,ld_in] C=K1, in2=b2 [B,H,W,ld_in2] K2,
+ *           in3=b3 [B,2H,2W,ld_in3] K3, in4=b4 [B,4H,4W,ld_in4] K4 (un-pooled tap);
+ *           w = [K1+K2+K3+K4][N] stacked 1x1 kernels (N=48), bias = alpha[4];
+ *           out[b,h,w,:] = a0*W1.b1[h/2,w/2] + a1*W2.b2[h,w]
+ *                        + a2*max_{2x2}(W3.b3) + a3*W4.max_{4x4}(b4)
+ *           (H,W = output grid).  rfcr_module + WeightedSum, model.py:117-157,190.
+ *  SE       in [B,H,W,ld_in] C=F channels; w = [F][R] then [R][F] (w2 = w + F*R),
+ *           bias = b1[R] then b2[F]; N = R; out = gate [B][F].
+ *           SEBlock, efficientnet.py:406-438.
+ */
+typedef struct yr_op {
+    int32_t kind;      /* yr_op_kind */
+    int32_t act;       /* yr_act */
+    int32_t mode;      /* yr_resample_mode (RESAMPLE) */
+    int32_t in_is_u8;  /* STEM */
+    int32_t B, H, W, C;      /* input batch / height / width / channels (K) */
+    int32_t Ho, Wo, N;       /* output height / width / channels */
+    int32_t k, stride, pad_t, pad_l;
+    int32_t ld_in, ld_in2, ld_in3, ld_in4, ld_out, ld_res;
+    int32_t K2, K3, K4;      /* RFCR: channels of in2..in4 */
+    int32_t variant;         /* PW kernel choice: 0 = auto, 1 = SIMT fp32, 2 = tcgen05 3xTF32 */
+    const void* in;
+    const void* in2;
+    const void* in3;
+    const void* in4;
+    void* out;
+    const float* w;
+    const float* bias;
+    const float* res;
+    const float* scale;
+} yr_op;
+
+/* Library identity / errors. */
+int yr_version(void);
+const char* yr_last_error(void);
+int yr_sizeof_op(void); /* sizeof(yr_op), for binding self-checks */
+
+/* Executes ops[0..n_ops) in order on `stream`.  The network forward
+ * (reference yolov3_body, code/yolo3/model.py:170-342, called from
+ * YoloModel.call code/yolo.py:152) is one call of this. */
+int yr_run_ops(const yr_op* ops, int n_ops, void* stream);
+
+/* ---- post-process: yolo_eval (reference code/yolo3/model.py:431-491) --------- */
+
+typedef struct yr_decode_params {
+    int32_t B;            /* images */
+    int32_t num_classes;  /* C */
+    int32_t num_scales;   /* 1..3, scales given coarse -> fine (s32, s16, s8) */
+    int32_t grid_h[3], grid_w[3];
+    int32_t ld[3];        /* element stride between grid cells of feats[s] (>= 3*(C+5)) */
+    float anchors[3][3][2]; /* per scale, per anchor: (w, h) in pixels - already masked
+                               with [[6,7,8],[3,4,5],[0,1,2]][-num_scales:] (model.py:444-445) */
+    int32_t input_h, input_w; /* network input = grid(s32) * 32 (model.py:449) */
+    float score_threshold;
+    int32_t cand_cap;     /* capacity of each (image,class) candidate list */
+} yr_decode_params;
+
+/* yolo_head + yolo_correct_boxes + yolo_boxes_and_scores (model.py:344-428) for a
+ * batch of independent images, fused with the score-threshold filter that
+ * tf.image.non_max_suppression applies internally.
+ *   feats[s]      [B,gh,gw,ld[s]] raw logits, cell layout (anchor, 5+C)
+ *   image_shapes  [B][2] float (h, w) of the ORIGINAL images (model.py:380-385)
+ *   boxes         [B][total_boxes][4] (ymin,xmin,ymax,xmax) image pixels
+ *   cand_score / cand_index [B][C][cand_cap]; cand_count [B][C] (zeroed by this call)
+ * Candidate (b,c) lists hold every box with conf*cls > score_threshold (strict),
+ * in unspecified order; counts saturate at cand_cap and the overflow is
+ * reported by yr_nms_classwise (never silently truncated). */
+int yr_decode_filter(const float* const feats[3], const float* image_shapes, const yr_decode_params* p,
+                     float* boxes, float* cand_score, int32_t* cand_index, int32_t* cand_count, void* stream);
+
+/* Class-wise greedy NMS == the `for c in range(num_classes):
+ * tf.image.non_max_suppression(...)` loop of model.py:474-486, bit-exact
+ * selection (score desc, ties -> lower index; IoU > thr strict; TF IoU formula).
+ *   det      [B][C][max_boxes][6] (ymin,xmin,ymax,xmax,score,box_index as float bits)
+ *   det_count[B][C]
+ *   status   [1] int32, set to 1 if any candidate list had overflowed cand_cap.
+ * cand_score is consumed (overwritten). */
+int yr_nms_classwise(const float* boxes, int total_boxes, float* cand_score, const int32_t* cand_index,
+                     const int32_t* cand_count, int B, int num_classes, int cand_cap, int max_boxes,
+                     float iou_threshold, float* det, int32_t* det_count, int32_t* status, void* stream);
+
+/* Concatenates per-class results class-major like model.py:487-490.
+ *   out_boxes_f [B][C*max_boxes][4] float, out_boxes_i same as int32 (truncated, model.py:490),
+ *   out_scores [B][C*max_boxes], out_classes [B][C*max_boxes] int32, out_count [B]. */
+int yr_pack_detections(const float* det, const int32_t* det_count, int B, int num_classes, int max_boxes,
+                       float* out_boxes_f, int32_t* out_boxes_i, float* out_scores, int32_t* out_classes,
+                       int32_t* out_count, void* stream);
+
+/* ---- pre-process: letterbox_image (reference code/yolo3/utils.py:67-83) ---------
+ * src u8 [ih,iw,3] -> dst f32 [h,w,3]: (1/255) scaling, bilinear half-pixel
+ * resize to (nh,nw), zero pad at (dy,dx).  nh/nw/dy/dx are computed by the
+ * host exactly as utils.py:76-79 does (float64). */
+int yr_letterbox_u8(const uint8_t* src, int ih, int iw, float* dst, int h, int w, int nh, int nw, int dy,
+                    int dx, void* stream);
+
+/* ---- training: YoloLoss (reference code/yolo3/model.py:585-671) ------------------
+ * One scale.  logits / y_true [B,gh,gw,A,5+C] with cell stride ld_logits / ld_true.
+ * true_boxes [n_true][4] = tf.boolean_mask(true_box, object_mask) over the WHOLE
+ * batch (model.py:643), produced by yr_yolo_loss_gather_true.
+ *   loss_parts [4]: giou, confidence, class sums (already / B) and sum(ignore_mask)
+ *   dlogits    same layout as logits (may be NULL for forward only):
+ *              d(loss)/d(logits) of giou+conf+class (ignore mask is a constant,
+ *              as in TF where tf.cast(bool) blocks the gradient).
+ * workspace: partials, >= yr_yolo_loss_workspace(...) bytes. */
+typedef struct yr_loss_params {
+    int32_t B, gh, gw, A, C;
+    int32_t ld_logits, ld_true; /* per-cell stride in elements, >= A*(5+C) */
+    float anchors[3][2];
+    int32_t input_h, input_w;
+    float ignore_thresh;
+    int32_t max_true;           /* capacity of true_boxes */
+} yr_loss_params;
+
+int64_t yr_yolo_loss_workspace(const yr_loss_params* p);
+int yr_yolo_loss_gather_true(const float* y_true, const yr_loss_params* p, float* true_boxes,
+                             int32_t* n_true, void* stream);
+int yr_yolo_loss(const float* logits, const float* y_true, const float* true_boxes, const int32_t* n_true,
+                 const yr_loss_params* p, float* loss_parts, float* dlogits, void* workspace,
+                 int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOLORET_B200_H_ */

@@ -245,9 +245,22 @@ def efficientnet(net: Net, x, model_name: str, lite: bool = False):
     x = net.conv(x, net.namer("conv2d"), _round_filters(32, width), k=3, s=2)
     x = a(net.bn(x, net.namer("batch_normalization")))
     stage_out = []
-    for (r, k, s, e, i, o, se) in _EFFNET_BLOCKS:
+    for si, (r, k, s, e, i, o, se) in enumerate(_EFFNET_BLOCKS):
         i, o, r = _round_filters(i, width), _round_filters(o, width), _round_repeats(r, depth)
         se = None if lite else se
+        if si == 6:
+            # stage 7 and the 1280-wide head conv are created by EfficientNet() but are not
+            # reachable from [y1,y2,y3] (taps end at stage 6), so Keras neither saves nor runs
+            # them; they only advance the auto-numbering.
+            for _ in range(r):
+                for _ in range((1 if e != 1 else 0) + (0 if se is None else 2) + 1):
+                    net.namer("conv2d")
+                net.namer("depthwise_conv2d")
+                for _ in range(3 if e != 1 else 2):
+                    net.namer("batch_normalization")
+            net.namer("conv2d")
+            net.namer("batch_normalization")
+            break
         x = mbconv_block(net, x, k, s, e, i, o, se, act)
         for _ in range(r - 1):
             x = mbconv_block(net, x, k, 1, e, o, o, se, act)
@@ -351,7 +364,7 @@ def yolov3_body(net: Net, inputs_nhwc: torch.Tensor, model_name: str, num_anchor
 
 
 # --------------------------------------------------------------------------
-# Weight spec + synthetic weights
+# Weight spec
 # --------------------------------------------------------------------------
 def weight_spec(model_name: str, num_classes: int, num_anchors: int = 3) -> "OrderedDict[str, Tuple[int, ...]]":
     """(name -> shape) of every weight, in creation order, for a config."""
@@ -359,64 +372,6 @@ def weight_spec(model_name: str, num_classes: int, num_anchors: int = 3) -> "Ord
     with torch.no_grad():
         yolov3_body(net, torch.zeros(1, 64, 64, 3), model_name, num_anchors, num_classes)
     return net.spec
-
-
-def synthetic_weights(model_name: str, num_classes: int, seed: int = 1234, num_anchors: int = 3,
-                      calibrate_head: bool = True) -> Dict[str, np.ndarray]:
-    """Seeded random-init weights of the named architecture.
-
-    conv / depthwise kernels: N(0, sqrt(2/fan_out)) as efficientnet.py:285-291;
-    SE biases small; BN statistics randomised (not identity) so BN folding is
-    exercised; WeightedSum alpha near 1 (model.py:127 initialises ones).
-    ``calibrate_head``: sets the beta of the three BNs feeding the y-convs so
-    that the mean objectness / class logits sit near -4 / -3 (SURVEY.md §8d's
-    synthetic-head statistics) -> a realistic ~1 % of boxes pass score 0.2.
-    """
-    rng = np.random.default_rng(seed)
-    spec = weight_spec(model_name, num_classes, num_anchors)
-    w: Dict[str, np.ndarray] = {}
-    for name, shape in spec.items():
-        leaf = name.split("/")[-1]
-        if leaf == "kernel":
-            kh, kw, _cin, cout = shape
-            w[name] = (rng.standard_normal(shape) * math.sqrt(2.0 / (kh * kw * cout))).astype(np.float32)
-        elif leaf == "depthwise_kernel":
-            kh, kw, c, _ = shape
-            # Keras fan_out for (kh,kw,C,1) would be kh*kw*1; use it as the reference does
-            w[name] = (rng.standard_normal(shape) * math.sqrt(2.0 / (kh * kw))).astype(np.float32) * 0.7
-        elif leaf == "bias":
-            w[name] = (rng.standard_normal(shape) * 0.1).astype(np.float32)
-        elif leaf == "gamma":
-            w[name] = rng.uniform(0.7, 1.3, shape).astype(np.float32)
-        elif leaf == "beta":
-            w[name] = rng.uniform(-0.2, 0.2, shape).astype(np.float32)
-        elif leaf == "moving_mean":
-            w[name] = rng.uniform(-0.2, 0.2, shape).astype(np.float32)
-        elif leaf == "moving_variance":
-            w[name] = rng.uniform(0.5, 1.5, shape).astype(np.float32)
-        elif leaf == "alpha":
-            w[name] = rng.uniform(0.6, 1.6, shape).astype(np.float32)
-        else:
-            raise ValueError(name)
-    if calibrate_head:
-        out = num_anchors * (num_classes + 5)
-        target = np.tile(np.concatenate([np.zeros(4), [-4.0], np.full(num_classes, -3.0)]), num_anchors)
-        names = list(spec.keys())
-        ykernels = [n for n in names if n.endswith("/kernel") and spec[n] == (1, 1, out, out)]
-        for yk in ykernels:
-            # BN that feeds this y-conv = last BN (with `out` channels) created before it
-            idx = names.index(yk)
-            beta = next(n for n in reversed(names[:idx]) if n.endswith("/beta") and spec[n] == (out,))
-            W = w[yk][0, 0].astype(np.float64)  # [cin, cout]
-            # tame the y-conv so logits have O(1) spread, then solve W^T b = target
-            W = W / max(1e-6, np.linalg.norm(W, axis=0).mean()) * 1.0
-            w[yk] = W[None, None].astype(np.float32)
-            b = np.linalg.lstsq(W.T, target, rcond=None)[0]
-            base = beta[: -len("/beta")]
-            w[beta] = b.astype(np.float32)
-            w[base + "/gamma"] = (w[base + "/gamma"] * 0.5).astype(np.float32)
-            w[base + "/moving_mean"] = np.zeros_like(w[base + "/moving_mean"])
-    return w
 
 
 def forward(weights: Dict[str, np.ndarray], x_nhwc, model_name: str, num_classes: int,

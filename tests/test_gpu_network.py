@@ -1,0 +1,145 @@
+"""GPU parity of the whole network / public API against the CPU oracle and the committed goldens."""
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from yoloret_b200.netdef import NetDef  # noqa: E402
+from yoloret_b200.weights import synthetic_weights  # noqa: E402
+from yoloret_b200.yolo3.model import yolov3_body, yolo_body  # noqa: E402
+from yoloret_b200.yolo import YOLO  # noqa: E402
+from yoloret_b200.yolo3.enums import BACKBONE  # noqa: E402
+from oracle import graph as ograph, postprocess as opp  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+# north_star tolerance: outputs within 1e-3 (fp32) of the reference CPU path
+TOL = 1e-3
+
+
+def _golden_weights():
+    z = np.load(os.path.join(GOLD, "voc_mbv2x75_weights.npz"))
+    return {k.replace("__", "/"): z[k] for k in z.files}
+
+
+@pytest.mark.parametrize("name,ncls,hw,B,micro", [
+    ("mobilenetv2x75", 20, (96, 96), 3, 2),       # micro-batching with a remainder chunk
+    ("mobilenetv2x75", 80, (128, 160), 2, None),  # non-square, COCO head width 255 -> 256
+    ("mobilenetv2x14", 80, (64, 64), 2, None),
+    ("efficientnetb3", 80, (64, 96), 2, None),
+    ("efficientnetlite0", 80, (64, 64), 2, 1),
+])
+def test_network_matches_oracle(built_lib, anchors, name, ncls, hw, B, micro):
+    nd = NetDef(name, ncls, hw)
+    w = synthetic_weights(nd.weight_shapes, ncls, seed=11)
+    x = torch.rand(B, hw[0], hw[1], 3, generator=torch.Generator().manual_seed(1234))
+    model = yolov3_body((B, hw[0], hw[1], 3), name, 3, num_classes=ncls, micro_batch=micro).set_weights(w, anchors)
+    ys = [y.cpu().numpy() for y in model(x.cuda())]
+    ref = [y.numpy() for y in ograph.forward(w, x, name, ncls)]
+    for s, (a, r) in enumerate(zip(ys, ref)):
+        assert a.shape == r.shape == (B, hw[0] // (32 >> s), hw[1] // (32 >> s), 3, ncls + 5)
+        err = np.abs(a - r).max()
+        assert err < TOL, "scale %d: max |diff| %g" % (s, err)
+    # pad channels of the padded output rows stay exactly zero
+    for v in model.engine.net.outputs:
+        t = model.engine.buf_t[v.buf.name]
+        assert float(t[..., 3 * (ncls + 5):].abs().max().item() if t.shape[-1] > 3 * (ncls + 5) else 0.0) == 0.0
+
+
+def test_u8_input_equals_float_input(built_lib, anchors):
+    hw, ncls, B = (96, 96), 20, 2
+    nd = NetDef("mobilenetv2x75", ncls, hw)
+    w = synthetic_weights(nd.weight_shapes, ncls, seed=3)
+    xi = torch.randint(0, 256, (B, hw[0], hw[1], 3), generator=torch.Generator().manual_seed(0), dtype=torch.uint8)
+    mf = yolo_body((B, hw[0], hw[1], 3), "mobilenetv2x75", 3, num_classes=ncls).set_weights(w, anchors)
+    mu = yolo_body((B, hw[0], hw[1], 3), "mobilenetv2x75", 3, num_classes=ncls, input_u8=True).set_weights(w, anchors)
+    yf = mf((xi.float() * np.float32(1.0 / 255.0)).cuda())
+    yu = mu(xi.cuda())
+    for a, b in zip(yf, yu):
+        assert torch.equal(a, b)
+
+
+def test_golden_head_logits(built_lib):
+    """Shipped VOC checkpoint + demo image 0/1: head logits vs the oracle's committed goldens."""
+    g = np.load(os.path.join(GOLD, "demo_golden.npz"))
+    w = _golden_weights()
+    from oracle import letterbox as olb
+    for i in range(2):
+        img = olb.decode_image_u8(g["jpeg_%d" % i].tobytes())
+        x = olb.letterbox_image(olb.u8_to_float(img), (320, 320))[None]
+        model = yolov3_body((1, 320, 320, 3), "mobilenetv2x75", 3, num_classes=20).set_weights(w, g["anchors"])
+        ys = model(torch.from_numpy(x).cuda())
+        for s, y in enumerate(ys):
+            ref = g["y%d_%d" % (s + 1, i)]
+            err = np.abs(y.cpu().numpy() - ref).max()
+            assert err < TOL, "image %d scale %d: %g" % (i, s, err)
+
+
+def test_detect_image_golden(built_lib, tmp_path):
+    """YOLO(FLAGS).detect_image(bytes, draw=False) on the 7 demo JPEGs == committed detections."""
+    g = np.load(os.path.join(GOLD, "demo_golden.npz"))
+    (tmp_path / "anchors.txt").write_text(",  ".join("%g,%g" % (a, b) for a, b in g["anchors"]))
+    classes = ["aeroplane", "bicycle", "bird", "boat", "bottle", "bus", "car", "cat", "chair", "cow", "diningtable",
+               "dog", "horse", "motorbike", "person", "pottedplant", "sheep", "sofa", "train", "tvmonitor"]
+    (tmp_path / "classes.txt").write_text("\n".join(classes) + "\n")
+    yolo = YOLO({"backbone": BACKBONE.MOBILENETV2x75, "classes_path": str(tmp_path / "classes.txt"),
+                 "anchors_path": str(tmp_path / "anchors.txt"), "input_size": (320, 320), "score": 0.3, "nms": 0.5,
+                 "weights": _golden_weights(), "model": "golden"})
+    n = len(g["names"])
+    for i in range(n):
+        data = g["jpeg_%d" % i].tobytes()
+        boxes, scores, cls = yolo.detect_image(io.BytesIO(data) if i % 2 else data, draw=False)
+        assert boxes.dtype == np.int32 and scores.dtype == np.float32 and cls.dtype == np.int32
+        assert np.array_equal(cls, g["det_classes_%d" % i]), (i, cls, g["det_classes_%d" % i])
+        np.testing.assert_allclose(scores, g["det_scores_%d" % i], atol=TOL)
+        assert np.abs(boxes.astype(np.int64) - g["det_boxes_i_%d" % i]).max(initial=0) <= 1
+    img = yolo.detect_image(g["jpeg_0"].tobytes(), draw=True)
+    assert img.size == (500, 375)
+
+
+def test_detect_batch_graph_equals_eager(built_lib, anchors, tmp_path):
+    hw, ncls, B = (96, 96), 20, 4
+    nd = NetDef("mobilenetv2x75", ncls, hw)
+    w = synthetic_weights(nd.weight_shapes, ncls, seed=5)
+    (tmp_path / "a.txt").write_text(",".join("%g,%g" % (a * 96 / 416, b * 96 / 416) for a, b in anchors))
+    (tmp_path / "c.txt").write_text("\n".join("c%d" % i for i in range(ncls)) + "\n")
+    yolo = YOLO({"backbone": "mobilenetv2x75", "classes_path": str(tmp_path / "c.txt"),
+                 "anchors_path": str(tmp_path / "a.txt"), "input_size": hw, "score": 0.05, "nms": 0.5, "weights": w,
+                 "batch": B, "input_u8": True, "micro_batch": 2})
+    xi = torch.randint(0, 256, (B, hw[0], hw[1], 3), generator=torch.Generator().manual_seed(0), dtype=torch.uint8)
+    eager = yolo.detect_batch(xi.pin_memory(), use_graph=False)
+    graph1 = yolo.detect_batch(xi.pin_memory(), use_graph=True)
+    graph2 = yolo.detect_batch(xi.pin_memory(), use_graph=True)
+    x = xi.float() * np.float32(1.0 / 255.0)
+    ref_ys = [y.numpy() for y in ograph.forward(w, x, "mobilenetv2x75", ncls)]
+    anc = np.loadtxt(str(tmp_path / "a.txt"), delimiter=",", dtype=np.float32).reshape(-1, 2)
+    total = 0
+    for b in range(B):
+        for a, c in ((eager[b], graph1[b]), (graph1[b], graph2[b])):
+            assert all(np.array_equal(p, q) for p, q in zip(a, c))
+        rb, rs, rc = opp.yolo_eval([r[b:b + 1] for r in ref_ys], anc, 3, ncls, hw, score_threshold=0.05,
+                                   iou_threshold=0.5)
+        gb, gs, gc = eager[b]
+        assert np.array_equal(gc, rc)
+        np.testing.assert_allclose(gs, rs, atol=TOL)
+        assert np.abs(gb.astype(np.int64) - rb).max(initial=0) <= 1
+        total += len(gs)
+    assert total > 0
+
+
+def test_api_errors(built_lib):
+    with pytest.raises(ValueError):
+        yolov3_body((1, 100, 100, 3), "mobilenetv2x75", 3, num_classes=20)  # not a multiple of 32
+    with pytest.raises(ValueError):
+        yolov3_body((1, 96, 96, 3), "resnet50", 3, num_classes=20)
+    with pytest.raises(ValueError):
+        yolov3_body((1, 96, 96, 3), "mobilenetv2x75", 3, num_classes=20, bogus_field=1)
+    m = yolov3_body((1, 96, 96, 3), "mobilenetv2x75", 3, num_classes=20)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 96, 96, 3, device="cuda"))
+    with pytest.raises(KeyError):
+        m.set_weights({})

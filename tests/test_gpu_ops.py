@@ -1,0 +1,212 @@
+"""GPU parity of the single-layer kernels against plain PyTorch fp32/fp64 references (through the C-ABI)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from yoloret_b200 import _lib  # noqa: E402
+from yoloret_b200._lib import YrOp  # noqa: E402
+from ophelp import run_op, act_ref, pw_op, ACT  # noqa: E402
+
+RTOL, ATOL = 2e-5, 2e-5  # fp32 kernels vs an fp64 reference of the same op
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale)
+
+
+@pytest.mark.parametrize("B,H,W,K,N,ld_in,act,use_res,use_scale", [
+    (2, 7, 9, 16, 8, 16, "none", False, False),
+    (2, 7, 9, 24, 24, 24, "relu6", True, False),
+    (3, 16, 16, 144, 24, 144, "none", True, False),
+    (1, 13, 13, 216, 512, 216, "relu6", False, False),
+    (2, 13, 13, 512, 80, 512, "none", False, True),
+    (2, 26, 26, 424, 256, 424, "relu6", False, False),
+    (1, 52, 52, 256, 256, 256, "none", False, False),
+    (2, 5, 5, 72, 72, 168, "swish", False, False),      # strided A (concat slice), N=72 tile
+    (2, 5, 5, 96, 144, 96, "swish", True, True),
+    (1, 3, 3, 720, 120, 720, "none", True, False),
+    (2, 9, 9, 48, 96, 48, "relu6", False, False),
+])
+def test_pw_parity(built_lib, B, H, W, K, N, ld_in, act, use_res, use_scale):
+    a = _rand(B, H, W, ld_in, seed=1)
+    w = _rand(K, N, seed=2, scale=K ** -0.5)
+    bias = _rand(N, seed=3)
+    res = _rand(B, H, W, N, seed=4) if use_res else None
+    scale = torch.rand(B, K, generator=torch.Generator().manual_seed(5)) if use_scale else None
+    ad = a[..., :K].double()
+    if use_scale:
+        ad = ad * scale.double()[:, None, None, :]
+    ref = act_ref(ad @ w.double() + bias.double(), act)
+    if use_res:
+        ref = ref + res.double()
+    out = pw_op(a.cuda(), w.cuda(), bias.cuda(), act, res.cuda() if use_res else None,
+                scale.cuda() if use_scale else None, ld_out=N + 8)
+    got = out[..., :N].cpu().double()
+    assert torch.isnan(out[..., N:]).all(), "kernel wrote outside its channel slice"
+    torch.testing.assert_close(got, ref, rtol=RTOL, atol=ATOL)
+
+
+def _same_pad_lead(size, k, s):
+    out = -(-size // s)
+    total = max((out - 1) * s + k - size, 0)
+    return out, total // 2, total - total // 2
+
+
+def _dw_ref(x, w, bias, k, s, act):
+    B, H, W, C = x.shape
+    Ho, pt, pb = _same_pad_lead(H, k, s)
+    Wo, pl, pr = _same_pad_lead(W, k, s)
+    xn = F.pad(x.permute(0, 3, 1, 2).double(), (pl, pr, pt, pb))
+    wn = w.reshape(k, k, C).permute(2, 0, 1)[:, None].double()
+    y = F.conv2d(xn, wn, bias.double(), stride=s, groups=C)
+    return act_ref(y, act).permute(0, 2, 3, 1), (Ho, Wo, pt, pl)
+
+
+@pytest.mark.parametrize("B,H,W,C,k,s,act", [
+    (2, 16, 16, 24, 3, 1, "relu6"),
+    (2, 16, 16, 96, 3, 2, "relu6"),    # even input: TF SAME pads (0,1)
+    (1, 13, 13, 720, 3, 1, "relu6"),   # odd input
+    (2, 13, 13, 432, 3, 2, "relu6"),   # odd input stride 2: pads (1,1)
+    (2, 26, 26, 48, 5, 1, "relu6"),
+    (1, 13, 13, 512, 3, 1, "swish"),
+    (2, 17, 11, 40, 5, 2, "swish"),
+    (1, 5, 3, 8, 3, 1, "none"),
+])
+def test_dw_parity(built_lib, B, H, W, C, k, s, act):
+    x = _rand(B, H, W, C, seed=1)
+    w = _rand(k * k, C, seed=2, scale=0.3)
+    bias = _rand(C, seed=3)
+    ref, (Ho, Wo, pt, pl) = _dw_ref(x, w, bias, k, s, act)
+    xd, wd, bd = x.cuda(), w.cuda(), bias.cuda()
+    out = torch.full((B, Ho, Wo, C), float("nan"), device="cuda")
+    op = YrOp()
+    op.kind, op.act = _lib.OP_DW, ACT[act]
+    op.B, op.H, op.W, op.C, op.Ho, op.Wo, op.N = B, H, W, C, Ho, Wo, C
+    op.k, op.stride, op.pad_t, op.pad_l, op.ld_in, op.ld_out = k, s, pt, pl, C, C
+    op.in_, op.out, op.w, op.bias = xd.data_ptr(), out.data_ptr(), wd.data_ptr(), bd.data_ptr()
+    run_op(op)
+    torch.testing.assert_close(out.cpu().double(), ref, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("u8", [False, True])
+@pytest.mark.parametrize("H,W,N,act", [(32, 32, 24, "relu6"), (33, 47, 40, "swish")])
+def test_stem_parity(built_lib, u8, H, W, N, act):
+    B = 2
+    g = torch.Generator().manual_seed(0)
+    if u8:
+        xi = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8)
+        x = xi.float() * np.float32(1.0 / 255.0)
+    else:
+        x = xi = torch.rand(B, H, W, 3, generator=g)
+    w = _rand(27, N, seed=2, scale=0.2)
+    bias = _rand(N, seed=3)
+    Ho, pt, pb = _same_pad_lead(H, 3, 2)
+    Wo, pl, pr = _same_pad_lead(W, 3, 2)
+    xn = F.pad(x.permute(0, 3, 1, 2).double(), (pl, pr, pt, pb))
+    wn = w.reshape(3, 3, 3, N).permute(3, 2, 0, 1).double()
+    ref = act_ref(F.conv2d(xn, wn, bias.double(), stride=2), act).permute(0, 2, 3, 1)
+    xd, wd, bd = xi.cuda(), w.cuda(), bias.cuda()
+    out = torch.full((B, Ho, Wo, N), float("nan"), device="cuda")
+    op = YrOp()
+    op.kind, op.act, op.in_is_u8 = _lib.OP_STEM, ACT[act], int(u8)
+    op.B, op.H, op.W, op.C, op.Ho, op.Wo, op.N = B, H, W, 3, Ho, Wo, N
+    op.k, op.stride, op.pad_t, op.pad_l, op.ld_in, op.ld_out = 3, 2, pt, pl, 3, N
+    op.in_, op.out, op.w, op.bias = xd.data_ptr(), out.data_ptr(), wd.data_ptr(), bd.data_ptr()
+    run_op(op)
+    torch.testing.assert_close(out.cpu().double(), ref, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("mode", ["up2", "pool2", "pool4"])
+def test_resample_exact(built_lib, mode):
+    B, H, W, C = 2, 8, 12, 24
+    x = _rand(B, H, W, C, seed=1)
+    xn = x.permute(0, 3, 1, 2)
+    if mode == "up2":
+        ref = xn.repeat_interleave(2, 2).repeat_interleave(2, 3)
+    else:
+        p = 2 if mode == "pool2" else 4
+        ref = F.max_pool2d(xn, p, p)
+    ref = ref.permute(0, 2, 3, 1)
+    Ho, Wo = ref.shape[1:3]
+    out = torch.full((B, Ho, Wo, C + 16), float("nan"), device="cuda")
+    xd = x.cuda()
+    op = YrOp()
+    op.kind, op.mode = _lib.OP_RESAMPLE, {"up2": 0, "pool2": 1, "pool4": 2}[mode]
+    op.B, op.H, op.W, op.C, op.Ho, op.Wo, op.N = B, H, W, C, Ho, Wo, C
+    op.ld_in, op.ld_out = C, C + 16
+    op.in_, op.out = xd.data_ptr(), out.data_ptr() + 8 * 4  # write into channel slice [8, 8+C)
+    run_op(op)
+    assert torch.equal(out[..., 8:8 + C].cpu(), ref)
+    assert torch.isnan(out[..., :8]).all() and torch.isnan(out[..., 8 + C:]).all()
+
+
+def test_rfcr_parity(built_lib):
+    B, H, W = 2, 6, 10  # stride-16 grid
+    K1, K2, K3, K4, N = 120, 72, 24, 24, 48
+    b1, b2 = _rand(B, H // 2, W // 2, K1, seed=1), _rand(B, H, W, K2, seed=2)
+    b3, b4 = _rand(B, 2 * H, 2 * W, K3, seed=3), _rand(B, 4 * H, 4 * W, K4, seed=4)
+    ws = [_rand(k, N, seed=10 + i, scale=k ** -0.5) for i, k in enumerate((K1, K2, K3, K4))]
+    alpha = torch.tensor([1.007, 1.663, -0.924, 0.589])  # a2 < 0 exercises the a2*max() order
+
+    def c(x, w):
+        return x.double() @ w.double()
+
+    def nchw(x):
+        return x.permute(0, 3, 1, 2)
+
+    up = nchw(c(b1, ws[0])).repeat_interleave(2, 2).repeat_interleave(2, 3)
+    p3 = F.max_pool2d(nchw(c(b3, ws[2])), 2, 2)
+    p4 = nchw(c(F.max_pool2d(nchw(b4), 4, 4).permute(0, 2, 3, 1), ws[3]))
+    a = alpha.double()
+    ref = (a[0] * up + a[1] * nchw(c(b2, ws[1])) + a[2] * p3 + a[3] * p4).permute(0, 2, 3, 1)
+    wcat = torch.cat(ws, 0).cuda()
+    d = [t.cuda() for t in (b1, b2, b3, b4)]
+    al = alpha.cuda()
+    out = torch.full((B, H, W, N), float("nan"), device="cuda")
+    op = YrOp()
+    op.kind = _lib.OP_RFCR
+    op.B, op.H, op.W, op.C, op.Ho, op.Wo, op.N = B, H // 2, W // 2, K1, H, W, N
+    op.K2, op.K3, op.K4 = K2, K3, K4
+    op.ld_in, op.ld_in2, op.ld_in3, op.ld_in4, op.ld_out = K1, K2, K3, K4, N
+    op.in_, op.in2, op.in3, op.in4 = (t.data_ptr() for t in d)
+    op.out, op.w, op.bias = out.data_ptr(), wcat.data_ptr(), al.data_ptr()
+    run_op(op)
+    torch.testing.assert_close(out.cpu().double(), ref, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("HW,F_,R", [((13, 13), 512, 128), ((7, 5), 128, 32), ((4, 4), 144, 6), ((3, 3), 1392, 58)])
+def test_se_parity(built_lib, HW, F_, R):
+    B = 3
+    x = _rand(B, HW[0], HW[1], F_, seed=1)
+    w1, b1 = _rand(F_, R, seed=2, scale=F_ ** -0.5), _rand(R, seed=3, scale=0.1)
+    w2, b2 = _rand(R, F_, seed=4, scale=R ** -0.5), _rand(F_, seed=5, scale=0.1)
+    m = x.double().mean(dim=(1, 2))
+    h = m @ w1.double() + b1.double()
+    h = h * torch.sigmoid(h)
+    ref = torch.sigmoid(h @ w2.double() + b2.double())
+    xd = x.cuda()
+    wcat = torch.cat([w1.reshape(-1), w2.reshape(-1)]).cuda()
+    bcat = torch.cat([b1, b2]).cuda()
+    out = torch.full((B, F_), float("nan"), device="cuda")
+    op = YrOp()
+    op.kind = _lib.OP_SE
+    op.B, op.H, op.W, op.C, op.N = B, HW[0], HW[1], F_, R
+    op.ld_in = F_
+    op.in_, op.out, op.w, op.bias = xd.data_ptr(), out.data_ptr(), wcat.data_ptr(), bcat.data_ptr()
+    run_op(op)
+    torch.testing.assert_close(out.cpu().double(), ref, rtol=RTOL, atol=ATOL)
+
+
+def test_bad_arguments_fail_loudly(built_lib):
+    op = YrOp()
+    op.kind = _lib.OP_PW
+    op.B, op.H, op.W, op.C, op.N = 1, 1, 1, 12, 8  # K not a multiple of 8, null pointers
+    ops = (YrOp * 1)(op)
+    rc = built_lib.yr_run_ops(ops, 1, None)
+    assert rc == -1 and b"pw" in built_lib.yr_last_error()
+    op.kind = 99
+    assert built_lib.yr_run_ops((YrOp * 1)(op), 1, None) == -1

@@ -1,0 +1,61 @@
+// Shared helpers for the yoloret_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/yoloret_b200.h"
+
+namespace yr {
+
+void set_error(const char* fmt, ...);
+
+#define YR_CHECK_ARG(cond, ...)                 \
+    do {                                        \
+        if (!(cond)) {                          \
+            yr::set_error(__VA_ARGS__);         \
+            return YR_ERR_INVALID;              \
+        }                                       \
+    } while (0)
+
+#define YR_CHECK_LAUNCH(what)                                                   \
+    do {                                                                        \
+        cudaError_t e__ = cudaGetLastError();                                   \
+        if (e__ != cudaSuccess) {                                               \
+            yr::set_error("%s: launch failed: %s", what, cudaGetErrorString(e__)); \
+            return YR_ERR_CUDA;                                                 \
+        }                                                                       \
+    } while (0)
+
+__host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Activations of the graph: ReLU6 (tf.keras.layers.ReLU(6.)) and Swish
+// (reference code/yolo3/efficientnet.py:327-331: x * sigmoid(x)).
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+template <int ACT>
+__device__ __forceinline__ float apply_act(float v) {
+    if (ACT == YR_ACT_RELU6) return fminf(fmaxf(v, 0.0f), 6.0f);
+    if (ACT == YR_ACT_SWISH) return v * (1.0f / (1.0f + expf(-v)));
+    return v;
+}
+
+__device__ __forceinline__ float apply_act_rt(float v, int act) {
+    if (act == YR_ACT_RELU6) return fminf(fmaxf(v, 0.0f), 6.0f);
+    if (act == YR_ACT_SWISH) return v * (1.0f / (1.0f + expf(-v)));
+    return v;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// per-op launchers (one .cu each)
+int launch_stem(const yr_op& op, cudaStream_t s);
+int launch_pw(const yr_op& op, cudaStream_t s);
+int launch_pw_tc(const yr_op& op, cudaStream_t s);
+int launch_dw(const yr_op& op, cudaStream_t s);
+int launch_resample(const yr_op& op, cudaStream_t s);
+int launch_rfcr(const yr_op& op, cudaStream_t s);
+int launch_se(const yr_op& op, cudaStream_t s);
+
+}  // namespace yr

@@ -1,0 +1,263 @@
+"""Device engine: lowers a ``NetDef`` to ``yr_op`` plans and runs them through the C-ABI.
+
+PyTorch is used for device memory, streams and CUDA-graph capture only; every
+arithmetic kernel on this path lives in ``csrc/`` behind ``include/yoloret_b200.h``.
+There is no CPU fallback: constructing an ``Engine`` without CUDA raises.
+
+Data layout in HBM: one activation arena sized for a
+micro-batch (reused across micro-batches so producer->consumer tensors stay
+L2-resident), full-batch head outputs y1..y3, and a post-process workspace
+(boxes, per-(image,class) candidate lists, per-class detections, packed output).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import YrOp, YrDecodeParams
+from .netdef import NetDef, Layer, View, pad_c
+from .postprocess import PostProcess
+
+BN_EPS = 1e-3  # every BatchNormalization in the reference graph
+_ACT = {"none": _lib.ACT_NONE, "relu6": _lib.ACT_RELU6, "swish": _lib.ACT_SWISH}
+_MODE = {"up2": _lib.UP2, "pool2": _lib.POOL2, "pool4": _lib.POOL4}
+
+
+def _fold_bn(w: Dict[str, np.ndarray], bn: Optional[str], cout: int):
+    """Returns per-output-channel (scale, bias) in float64."""
+    if bn is None:
+        return np.ones(cout), np.zeros(cout)
+    g = w[bn + "/gamma"].astype(np.float64)
+    b = w[bn + "/beta"].astype(np.float64)
+    m = w[bn + "/moving_mean"].astype(np.float64)
+    v = w[bn + "/moving_variance"].astype(np.float64)
+    s = g / np.sqrt(v + BN_EPS)
+    return s, b - m * s
+
+
+def _expand_rows(mat: np.ndarray, segs) -> np.ndarray:
+    """[sum(logical), N] -> [sum(padded), N] with zero rows at the pad positions."""
+    out = np.zeros((sum(p for _, p in segs), mat.shape[1]), dtype=mat.dtype)
+    ri = ro = 0
+    for l, p in segs:
+        out[ro:ro + l] = mat[ri:ri + l]
+        ri += l
+        ro += p
+    return out
+
+
+def _pad_cols(mat: np.ndarray, n_pad: int) -> np.ndarray:
+    out = np.zeros(mat.shape[:-1] + (n_pad,), dtype=mat.dtype)
+    out[..., :mat.shape[-1]] = mat
+    return out
+
+
+class Engine:
+    def __init__(self, model_name: str, num_classes: int, input_hw: Tuple[int, int], batch: int,
+                 weights: Dict[str, np.ndarray], anchors: np.ndarray, micro_batch: Optional[int] = None,
+                 num_scales: int = 3, max_boxes: int = 20, cand_cap: Optional[int] = None,
+                 device: Optional[torch.device] = None, pw_variant: int = _lib.PW_AUTO, input_u8: bool = False):
+        if not torch.cuda.is_available():
+            raise _lib.YrError("yoloret_b200.Engine needs a CUDA device (no CPU fallback exists)")
+        self.lib = _lib.lib()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.net = NetDef(model_name, num_classes, input_hw)
+        self.model_name, self.num_classes, self.input_hw = model_name, num_classes, tuple(input_hw)
+        self.batch = int(batch)
+        self.micro = int(micro_batch) if micro_batch else self.batch
+        self.num_scales, self.max_boxes = num_scales, max_boxes
+        self.anchors = np.asarray(anchors, dtype=np.float32).reshape(-1, 2)
+        self.input_u8 = input_u8
+        self.pw_variant = pw_variant
+        self.cand_cap_arg = cand_cap
+        self._check_weights(weights)
+        self._alloc()
+        self._prep_weights(weights)
+        self._plans: Dict[Tuple[int, int], Tuple] = {}
+        self._graph = None
+        self.launches_per_forward = 0
+
+    # ---- setup -----------------------------------------------------------------
+    def _check_weights(self, w):
+        for name, shape in self.net.weight_shapes.items():
+            if name not in w:
+                raise KeyError("missing weight %s" % name)
+            if tuple(w[name].shape) != tuple(shape):
+                raise ValueError("weight %s has shape %s, expected %s" % (name, w[name].shape, shape))
+
+    def _alloc(self):
+        net, dev = self.net, self.device
+        self.buf_t: Dict[str, torch.Tensor] = {}
+        offs, total = {}, 0
+        for b in net.bufs:
+            if b.full_batch:
+                continue
+            n = self.micro * b.H * b.W * b.ld
+            offs[b.name] = total
+            total += (n + 63) // 64 * 64
+        self.arena = torch.zeros(total, dtype=torch.float32, device=dev)
+        for b in net.bufs:
+            if b.full_batch:
+                self.buf_t[b.name] = torch.zeros(self.batch, b.H, b.W, b.ld, dtype=torch.float32, device=dev)
+            else:
+                n = self.micro * b.H * b.W * b.ld
+                self.buf_t[b.name] = self.arena[offs[b.name]:offs[b.name] + n].view(self.micro, b.H, b.W, b.ld)
+        self.arena_bytes = total * 4
+        in_dtype = torch.uint8 if self.input_u8 else torch.float32
+        self.input = torch.zeros(self.batch, self.input_hw[0], self.input_hw[1], 3, dtype=in_dtype, device=dev)
+        grids = [(v.H, v.W) for v in net.outputs]
+        self.pp = PostProcess(self.batch, grids, self.num_classes, self.anchors, self.num_scales, self.max_boxes,
+                              device=dev, cand_cap=self.cand_cap_arg)
+        self.total_boxes = self.pp.total_boxes
+
+    def _dev(self, arr: np.ndarray) -> torch.Tensor:
+        return torch.from_numpy(np.ascontiguousarray(arr.astype(np.float32))).to(self.device)
+
+    def _prep_weights(self, w):
+        """Folds BN, pads channels to the device layout and uploads."""
+        self.wdev: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
+        for i, L in enumerate(self.net.layers):
+            if L.kind == "pw":
+                k = w[L.conv + "/kernel"][0, 0].astype(np.float64)          # [Cin, Cout]
+                s, b = _fold_bn(w, L.bn, k.shape[1])
+                mat = _pad_cols(_expand_rows(k * s[None, :], L.inp[0].segs), L.out.C)
+                self.wdev[i] = (self._dev(mat), self._dev(_pad_cols(b, L.out.C)))
+            elif L.kind == "dw":
+                k = w[L.conv + "/depthwise_kernel"][:, :, :, 0].astype(np.float64)  # [k,k,C]
+                s, b = _fold_bn(w, L.bn, k.shape[2])
+                mat = _pad_cols((k * s[None, None, :]).reshape(L.k * L.k, -1), L.out.C)
+                self.wdev[i] = (self._dev(mat), self._dev(_pad_cols(b, L.out.C)))
+            elif L.kind == "stem":
+                k = w[L.conv + "/kernel"].astype(np.float64)                # [3,3,3,Cout]
+                s, b = _fold_bn(w, L.bn, k.shape[3])
+                mat = _pad_cols((k * s).reshape(27, -1), L.out.C)
+                self.wdev[i] = (self._dev(mat), self._dev(_pad_cols(b, L.out.C)))
+            elif L.kind == "se":
+                c1, c2, R = L.extra["conv1"], L.extra["conv2"], L.extra["reduced"]
+                w1 = _expand_rows(w[c1 + "/kernel"][0, 0].astype(np.float64), L.inp[0].segs)      # [Fp, R]
+                w2 = _pad_cols(w[c2 + "/kernel"][0, 0].astype(np.float64), L.inp[0].C)            # [R, Fp]
+                b2 = _pad_cols(w[c2 + "/bias"].astype(np.float64), L.inp[0].C)
+                wcat = np.concatenate([w1.ravel(), w2.ravel()])
+                bcat = np.concatenate([w[c1 + "/bias"].astype(np.float64), b2])
+                self.wdev[i] = (self._dev(wcat), self._dev(bcat))
+            elif L.kind == "rfcr":
+                mats = [_expand_rows(w[cn + "/kernel"][0, 0].astype(np.float64), v.segs)
+                        for cn, v in zip(L.extra["convs"], L.inp)]
+                mat = _pad_cols(np.concatenate(mats, 0), L.out.C)
+                self.wdev[i] = (self._dev(mat), self._dev(w["weighted_sum/alpha"]))
+        self.weight_bytes = sum(a.numel() * 4 + b.numel() * 4 for a, b in self.wdev.values())
+
+    # ---- plan ---------------------------------------------------------------------
+    def _ptr(self, v: View, chunk0: int) -> int:
+        """Device address of a view for the micro-batch starting at image ``chunk0``."""
+        t = self.input if v.buf.name == "input" else self.buf_t[v.buf.name]
+        base = t.data_ptr() + v.off * t.element_size()
+        if v.buf.full_batch:
+            base += chunk0 * v.buf.H * v.buf.W * v.buf.ld * t.element_size()
+        return base
+
+    def build_plan(self, chunk0: int, nb: int):
+        """yr_op array for images [chunk0, chunk0+nb)."""
+        key = (chunk0, nb)
+        if key in self._plans:
+            return self._plans[key]
+        ops = (YrOp * len(self.net.layers))()
+        gate_ptr: Dict[int, int] = {}
+        for i, L in enumerate(self.net.layers):
+            o = ops[i]
+            x = L.inp[0]
+            o.act = _ACT[L.act]
+            o.B, o.H, o.W, o.C = nb, x.H, x.W, x.C
+            o.Ho, o.Wo, o.N = L.out.H, L.out.W, L.out.C
+            o.k, o.stride = L.k, L.stride
+            o.pad_t, o.pad_l = L.extra.get("pad_t", 0), L.extra.get("pad_l", 0)
+            o.ld_in, o.ld_out = x.buf.ld, L.out.buf.ld
+            o.in_ = self._ptr(x, chunk0)
+            o.out = self._ptr(L.out, chunk0)
+            if i in self.wdev:
+                o.w, o.bias = self.wdev[i][0].data_ptr(), self.wdev[i][1].data_ptr()
+            if L.kind == "stem":
+                o.kind = _lib.OP_STEM
+                o.C = 3
+                o.in_is_u8 = 1 if self.input_u8 else 0
+            elif L.kind == "pw":
+                o.kind = _lib.OP_PW
+                o.variant = self.pw_variant
+                if L.res is not None:
+                    o.res, o.ld_res = self._ptr(L.res, chunk0), L.res.buf.ld
+                if L.gate is not None:
+                    o.scale = gate_ptr[id(L.gate)]
+            elif L.kind == "dw":
+                o.kind = _lib.OP_DW
+            elif L.kind == "resample":
+                o.kind = _lib.OP_RESAMPLE
+                o.mode = _MODE[L.mode]
+            elif L.kind == "se":
+                o.kind = _lib.OP_SE
+                o.N = L.extra["reduced"]
+                gate_ptr[id(L)] = o.out
+            elif L.kind == "rfcr":
+                o.kind = _lib.OP_RFCR
+                b1, b2, b3, b4 = L.inp
+                o.C, o.K2, o.K3, o.K4 = b1.C, b2.C, b3.C, b4.C
+                o.ld_in, o.ld_in2, o.ld_in3, o.ld_in4 = b1.buf.ld, b2.buf.ld, b3.buf.ld, b4.buf.ld
+                o.in_, o.in2, o.in3, o.in4 = (self._ptr(v, chunk0) for v in (b1, b2, b3, b4))
+            else:
+                raise ValueError(L.kind)
+        self._plans[key] = (ops, len(self.net.layers))
+        return self._plans[key]
+
+    # ---- execution ------------------------------------------------------------------
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def run_network(self):
+        """yolov3_body forward over self.input -> y buffers, micro-batch by micro-batch."""
+        st = self._stream()
+        n = 0
+        for c0 in range(0, self.batch, self.micro):
+            nb = min(self.micro, self.batch - c0)
+            ops, cnt = self.build_plan(c0, nb)
+            _lib.check(self.lib.yr_run_ops(ops, cnt, st), "yr_run_ops")
+            n += cnt
+        return n
+
+    def raw_outputs(self) -> List[torch.Tensor]:
+        """[y1, y2, y3] as [B, gh, gw, A, C+5] strided views of the padded buffers."""
+        E = self.num_classes + 5
+        outs = []
+        for v in self.net.outputs:
+            t = self.buf_t[v.buf.name]
+            ld = v.buf.ld
+            outs.append(t.as_strided((self.batch, v.H, v.W, 3, E), (v.H * v.W * ld, v.W * ld, ld, E, 1)))
+        return outs
+
+    def run_postprocess(self, score_threshold: float, iou_threshold: float) -> int:
+        """yolo_eval (model.py:431-491) on the y buffers."""
+        ptrs = [self.buf_t[v.buf.name].data_ptr() for v in self.net.outputs[:self.num_scales]]
+        ld = [v.buf.ld for v in self.net.outputs[:self.num_scales]]
+        return self.pp.run(ptrs, ld, score_threshold, iou_threshold, self._stream())
+
+    def step(self, score_threshold: float, iou_threshold: float) -> int:
+        """One full pass: network + post-process on whatever is in self.input. Returns #kernel launches."""
+        n = self.run_network()
+        self.run_postprocess(score_threshold, iou_threshold)
+        self.launches_per_forward = n + 3
+        return n + 3
+
+    def capture(self, score_threshold: float, iou_threshold: float):
+        """Captures step() into a CUDA graph (launch-bound at small batch: ~90 kernels / micro-batch)."""
+        self.step(score_threshold, iou_threshold)  # warm-up: sets func attributes outside capture
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.step(score_threshold, iou_threshold)
+        self._graph = g
+        return g
+
+    def results(self, with_float_boxes: bool = False):
+        return self.pp.results(with_float_boxes)

@@ -1,0 +1,258 @@
+"""Host-side mirror of reference code/yolo3/model.py on the B200 engine.
+
+Same names, argument meaning and error behaviour as the reference functions; tensors
+are CUDA ``torch.Tensor``s instead of ``tf.Tensor``s, and every arithmetic step runs in
+the CUDA library behind include/yoloret_b200.h (no CPU fallback).
+
+  yolov3_body / yolo_body   reference code/yolo3/model.py:170-342
+  yolo_eval / YoloEval      code/yolo3/model.py:431-526
+  YoloLoss / yolo_loss      code/yolo3/model.py:585-671 (+ AdvLossModel._compute_total_loss,
+                            code/yolo3/train.py:11-16)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .._lib import YrLossParams
+from ..engine import Engine
+from ..postprocess import PostProcess, ANCHOR_MASK
+from ..weights import load_checkpoint
+from .enums import BOX_LOSS
+
+_BACKBONES = ("mobilenetv2x75", "mobilenetv2x14", "efficientnetb3", "efficientnetlite0")
+_GLOBAL_PARAM_FIELDS = ("batch_norm_momentum", "batch_norm_epsilon", "dropout_rate", "data_format", "num_classes",
+                        "width_coefficient", "depth_coefficient", "depth_divisor", "min_depth", "drop_connect_rate")
+
+
+class YoloBody:
+    """What ``yolov3_body`` returns: callable ``model(x) -> [y1, y2, y3]`` with
+    ``load_weights`` / ``set_weights`` (reference: an ``AdvLossModel``, model.py:342)."""
+
+    def __init__(self, input_shape, model_name, num_anchors, num_classes, micro_batch=None, device=None,
+                 pw_variant=_lib.PW_AUTO, input_u8=False, num_scales=3):
+        self.batch, self.input_hw = int(input_shape[0]), (int(input_shape[1]), int(input_shape[2]))
+        self.model_name, self.num_anchors, self.num_classes = model_name, num_anchors, num_classes
+        self._kw = dict(micro_batch=micro_batch, device=device, pw_variant=pw_variant, input_u8=input_u8,
+                        num_scales=num_scales)
+        self.engine: Optional[Engine] = None
+        from ..netdef import NetDef
+        self.netdef = NetDef(model_name, num_classes, self.input_hw, num_anchors)
+        self.anchors = np.zeros((9, 2), np.float32)
+
+    @property
+    def weight_shapes(self):
+        return self.netdef.weight_shapes
+
+    def set_weights(self, weights: Dict[str, np.ndarray], anchors=None):
+        if anchors is not None:
+            self.anchors = np.asarray(anchors, np.float32).reshape(-1, 2)
+        self.engine = Engine(self.model_name, self.num_classes, self.input_hw, self.batch, weights, self.anchors,
+                             **self._kw)
+        return self
+
+    def load_weights(self, path: str, by_name: bool = False, anchors=None):
+        """reference: model.load_weights(path) (code/yolo.py:87, code/yolo3/utils.py:390)."""
+        return self.set_weights(load_checkpoint(path, self.netdef.weight_shapes), anchors)
+
+    def __call__(self, x: torch.Tensor) -> List[torch.Tensor]:
+        if self.engine is None:
+            raise RuntimeError("weights not loaded: call load_weights()/set_weights() first")
+        e = self.engine
+        if tuple(x.shape) != tuple(e.input.shape):
+            raise ValueError("input shape %s != model input %s" % (tuple(x.shape), tuple(e.input.shape)))
+        if x.dtype != e.input.dtype:
+            raise ValueError("input dtype %s != model input dtype %s" % (x.dtype, e.input.dtype))
+        e.input.copy_(x, non_blocking=True)
+        e.run_network()
+        return e.raw_outputs()
+
+
+def yolov3_body(inputs, model_name, num_anchors, **kwargs):
+    """reference code/yolo3/model.py:170.  ``inputs``: a (B,H,W,3) shape or a tensor of that shape
+    (the reference passes a Keras Input).  kwargs are the GlobalParams overrides the reference
+    accepts (``num_classes``, ``data_format``, ... ; ``drop_rate`` is dropped as in
+    efficientnet.py:260-261) plus engine options (``micro_batch``, ``device``, ``pw_variant``,
+    ``input_u8``)."""
+    shape = tuple(inputs.shape) if hasattr(inputs, "shape") else tuple(inputs)
+    if len(shape) != 4 or shape[3] != 3:
+        raise ValueError("inputs must be (B,H,W,3) channels_last, got %s" % (shape,))
+    kwargs = dict(kwargs)
+    kwargs.pop("drop_rate", None)
+    eng = {k: kwargs.pop(k) for k in ("micro_batch", "device", "pw_variant", "input_u8", "num_scales")
+           if k in kwargs}
+    for k in kwargs:
+        if k not in _GLOBAL_PARAM_FIELDS:  # namedtuple._replace raises ValueError in the reference
+            raise ValueError("Got unexpected field names: %r" % [k])
+    if kwargs.get("data_format", "channels_last") != "channels_last":
+        raise ValueError("only data_format='channels_last' is supported (reference code/yolo.py:208)")
+    if model_name not in _BACKBONES:
+        raise ValueError("unknown model_name %r" % (model_name,))
+    return YoloBody(shape, model_name, num_anchors, kwargs.get("num_classes", 1000), **eng)
+
+
+yolo_body = yolov3_body  # spelling used by BASELINE.json's north_star
+
+
+# --------------------------------------------------------------------------------------
+_pp_cache: Dict[Tuple, PostProcess] = {}
+
+
+def _as_cells(t: torch.Tensor, num_classes: int) -> Tuple[torch.Tensor, int]:
+    """Accepts [B,gh,gw,A,5+C] (contiguous or a padded-row strided view) -> (tensor, cell stride)."""
+    if not t.is_cuda or t.dtype != torch.float32 or t.dim() != 5:
+        raise ValueError("yolo outputs must be float32 CUDA tensors [B,gh,gw,A,5+C]")
+    E = num_classes + 5
+    if t.shape[4] != E or t.shape[3] != 3:
+        raise ValueError("expected [...,3,%d], got %s" % (E, tuple(t.shape)))
+    st = t.stride()
+    ok = st[4] == 1 and st[3] == E and st[1] == t.shape[2] * st[2] and st[0] == t.shape[1] * st[1] and st[2] >= 3 * E
+    if not ok:
+        t = t.contiguous()
+        st = t.stride()
+    return t, st[2]
+
+
+def yolo_eval(yolo_outputs, anchors, num_scales, num_classes, image_shape, max_boxes=20, score_threshold=.6,
+              iou_threshold=.5, zoom_outputs=None):
+    """reference code/yolo3/model.py:431.  Returns (boxes_ int32 [N,4] (ymin,xmin,ymax,xmax),
+    scores_ f32 [N], classes_ int32 [N]) as CUDA tensors for a batch of one (as the reference);
+    for B > 1 returns per-image lists (batch = independent per-image application)."""
+    if zoom_outputs is not None:
+        raise NotImplementedError("zoom_outputs is an unused experiment in the reference (model.py:408-417)")
+    feats, lds = [], []
+    for t in yolo_outputs[:num_scales]:
+        t, ld = _as_cells(t, num_classes)
+        feats.append(t)
+        lds.append(ld)
+    B = feats[0].shape[0]
+    grids = tuple((int(t.shape[1]), int(t.shape[2])) for t in feats)
+    key = (B, grids, num_classes, num_scales, max_boxes, feats[0].device.index, np.asarray(anchors).tobytes())
+    pp = _pp_cache.get(key)
+    if pp is None:
+        if len(_pp_cache) > 8:
+            _pp_cache.clear()
+        pp = _pp_cache[key] = PostProcess(B, grids, num_classes, anchors, num_scales, max_boxes,
+                                          device=feats[0].device)
+    pp.set_image_shapes(image_shape)
+    pp.run([t.data_ptr() for t in feats], lds, score_threshold, iou_threshold)
+    cnt = pp.out_count.cpu().numpy()
+    if int(pp.status.item()) != 0:
+        raise _lib.YrError("candidate list overflow")
+    res = [(pp.out_boxes_i[b, :n].clone(), pp.out_scores[b, :n].clone(), pp.out_classes[b, :n].clone())
+           for b, n in enumerate(cnt)]
+    return res[0] if B == 1 else res
+
+
+class YoloEval:
+    """reference code/yolo3/model.py:494-526 (a Keras layer wrapper of yolo_eval)."""
+
+    def __init__(self, anchors, num_scales, num_classes, max_boxes=20, score_threshold=.6, iou_threshold=.5, **kwargs):
+        self.anchors, self.num_scales, self.num_classes = anchors, num_scales, num_classes
+        self.max_boxes, self.score_threshold, self.iou_threshold = max_boxes, score_threshold, iou_threshold
+
+    def __call__(self, yolo_outputs, image_shape, zoom_outputs=None):
+        return yolo_eval(yolo_outputs, self.anchors, self.num_scales, self.num_classes, image_shape, self.max_boxes,
+                         self.score_threshold, self.iou_threshold, zoom_outputs=zoom_outputs)
+
+    call = __call__
+
+    def get_config(self):
+        return dict(anchors=self.anchors, num_scales=self.num_scales, num_classes=self.num_classes,
+                    max_boxes=self.max_boxes, score_threshold=self.score_threshold,
+                    iou_threshold=self.iou_threshold)
+
+
+# --------------------------------------------------------------------------------------
+class _YoloLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, yolo_output, y_true, loss_obj):
+        parts, dlogits = loss_obj._run(y_true, yolo_output, need_grad=yolo_output.requires_grad)
+        ctx.dlogits = dlogits
+        loss_obj.last_parts = parts
+        return parts[0] + parts[1] + parts[2]  # giou + confidence + class, model.py:669
+
+    @staticmethod
+    def backward(ctx, g):
+        return (ctx.dlogits * g if ctx.dlogits is not None else None), None, None
+
+
+class YoloLoss:
+    """reference code/yolo3/model.py:585.  One instance per scale ``idx`` (strides 32,16,8).
+    ``loss(y_true, yolo_output)`` returns a scalar CUDA tensor wired into torch autograd:
+    ``.backward()`` delivers the fused kernel's analytic d(loss)/d(yolo_output)."""
+
+    def __init__(self, idx, anchors, num_scales, ignore_thresh=.5, box_loss=BOX_LOSS.GIOU, print_loss=True):
+        grid_steps = [32, 16, 8]
+        anchor_masks = ANCHOR_MASK[-1 * num_scales:]
+        self.idx, self.ignore_thresh, self.box_loss, self.print_loss = idx, ignore_thresh, box_loss, print_loss
+        self.grid_step = grid_steps[idx]
+        self.anchor = np.asarray(anchors, np.float32).reshape(-1, 2)[anchor_masks[idx]]
+        if box_loss != BOX_LOSS.GIOU:
+            # the reference's MSE branch references undefined names and would raise (model.py:672-690)
+            raise NameError("BOX_LOSS.MSE is dead code in the reference (undefined names); only GIOU is supported")
+        self.last_parts = None
+
+    def _run(self, y_true: torch.Tensor, yolo_output: torch.Tensor, need_grad: bool):
+        lib = _lib.lib()
+        if not (yolo_output.is_cuda and y_true.is_cuda):
+            raise _lib.YrError("YoloLoss needs CUDA tensors (no CPU fallback exists)")
+        B, gh, gw, A, E = (int(v) for v in yolo_output.shape)
+        logits, ldl = yolo_output.detach().contiguous(), A * E
+        ytrue, ldt = _as_cells_generic(y_true.detach().to(torch.float32), A, E)
+        p = YrLossParams()
+        p.B, p.gh, p.gw, p.A, p.C = B, gh, gw, A, E - 5
+        p.ld_logits, p.ld_true = ldl, ldt
+        for k in range(A):
+            p.anchors[k][0], p.anchors[k][1] = float(self.anchor[k][0]), float(self.anchor[k][1])
+        p.input_h, p.input_w = gh * self.grid_step, gw * self.grid_step  # model.py:628
+        p.ignore_thresh = float(self.ignore_thresh)
+        p.max_true = B * gh * gw * A
+        dev = logits.device
+        st = torch.cuda.current_stream(dev).cuda_stream
+        true_boxes = torch.empty(max(1, p.max_true), 4, dtype=torch.float32, device=dev)
+        n_true = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws_bytes = int(lib.yr_yolo_loss_workspace(C.byref(p)))
+        ws = torch.empty(max(4, ws_bytes // 4), dtype=torch.float32, device=dev)
+        parts = torch.empty(4, dtype=torch.float32, device=dev)
+        dl = None
+        if need_grad:
+            dl = torch.empty_like(logits)
+        _lib.check(lib.yr_yolo_loss_gather_true(ytrue.data_ptr(), C.byref(p), true_boxes.data_ptr(),
+                                                n_true.data_ptr(), st), "yr_yolo_loss_gather_true")
+        _lib.check(lib.yr_yolo_loss(logits.data_ptr(), ytrue.data_ptr(), true_boxes.data_ptr(), n_true.data_ptr(),
+                                    C.byref(p), parts.data_ptr(), dl.data_ptr() if dl is not None else None,
+                                    ws.data_ptr(), ws.numel() * 4, st), "yr_yolo_loss")
+        if self.print_loss:  # tf.print(idx, giou, conf, class, sum(ignore)), model.py:670-671
+            v = parts.cpu().numpy()
+            print("%d: %s %s %s %s" % (self.idx, v[0], v[1], v[2], v[3]))
+        return parts, dl
+
+    def __call__(self, y_true, yolo_output):
+        return _YoloLossFn.apply(yolo_output, y_true, self)
+
+    call = __call__
+
+
+def _as_cells_generic(t: torch.Tensor, A: int, E: int):
+    st = t.stride()
+    ok = (t.dim() == 5 and st[4] == 1 and st[3] == E and st[1] == t.shape[2] * st[2]
+          and st[0] == t.shape[1] * st[1] and st[2] >= A * E)
+    if not ok:
+        t = t.contiguous()
+        st = t.stride()
+    return t, st[2]
+
+
+def yolo_loss(y_trues: Sequence[torch.Tensor], yolo_outputs: Sequence[torch.Tensor], anchors, num_scales=3,
+              ignore_thresh=.5, box_loss=BOX_LOSS.GIOU, print_loss=False) -> torch.Tensor:
+    """Functional form named by BASELINE.json: the sum over scales of the per-scale YoloLoss,
+    exactly as AdvLossModel._compute_total_loss does (reference code/yolo3/train.py:11-16)."""
+    loss = 0
+    for idx, (yt, yo) in enumerate(zip(y_trues, yolo_outputs)):
+        loss = loss + YoloLoss(idx, anchors, num_scales, ignore_thresh, box_loss, print_loss)(yt, yo)
+    return loss
