@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""Headline benchmark: images/sec of the YOLO-ReT detection hot path at 416x416.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path (yolov3_body forward -> yolo_eval: decode, class-wise NMS,
+packing) over one batch of synthetic input.  Workload = BASELINE.json configs[1]:
+MobileNetV2-0.75x, 416x416, COCO-80 classes, batch 64 per GPU, seeded random-init weights,
+``torch.rand`` images.  Multi-GPU shards the batch (64 images per rank, weak scaling) and ends
+every step with an NCCL all-gather of the packed detections.
+
+Keys of the JSON line (see the task contract):
+  value     images/s, inputs resident in HBM, one CUDA-graph replay (+ all-gather) per step
+  e2e       images/s through ``YOLO.detect_batch`` with pinned HOST fp32 images: host->device
+            copy, the same graph, device->host read of the packed detections, every step
+  roofline  the dominant kernel (largest share of the step): algorithmic bytes / CUDA-event time
+  cpu_baseline  the torch-CPU oracle (restatement of the reference TF graph; TF is not
+            installable here) on the host cores, bounded sample
+``--impl reference`` times that same oracle as the reference arm (the reference is pure Python on
+TensorFlow, which is not installed in this image - see DESIGN.md).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ANCHORS = [10, 13, 16, 30, 33, 23, 30, 61, 62, 45, 59, 119, 116, 90, 156, 198, 373, 326]
+METRIC = "images/sec at 416x416"
+UNIT = "images/s"
+SCORE, IOU = 0.2, 0.5  # YOLO defaults, reference code/yolo.py:176-177
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="mobilenetv2x75")
+    ap.add_argument("--size", type=int, default=416)
+    ap.add_argument("--classes", type=int, default=80)
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--micro", type=int, default=0, help="micro-batch (0 = engine default)")
+    ap.add_argument("--pw-variant", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--ref-images", type=int, default=4, help="images per step of the reference arm")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (profiling recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 0))), "measured"
+    return 6650.0, 1400.0, "fallback"
+
+
+def workload_name(a):
+    return "%s %dx%d %d-class inference, batch=%d per GPU" % (a.model, a.size, a.size, a.classes, a.batch)
+
+
+def make_inputs(a, batch, seed):
+    import torch
+    return torch.rand(batch, a.size, a.size, 3, generator=torch.Generator().manual_seed(seed))
+
+
+def make_weights(a):
+    from yoloret_b200.netdef import NetDef
+    from yoloret_b200.weights import synthetic_weights
+    nd = NetDef(a.model, a.classes, (a.size, a.size))
+    return nd, synthetic_weights(nd.weight_shapes, a.classes, seed=1234)
+
+
+# ---------------------------------------------------------------------------------------------
+def oracle_step(weights, x, a, anchors):
+    """The CPU restatement of the hot path on a batch: network + per-image yolo_eval."""
+    from oracle import graph as ograph, postprocess as opp
+    ys = [y.numpy() for y in ograph.forward(weights, x, a.model, a.classes)]
+    n = 0
+    for b in range(x.shape[0]):
+        _, s, _ = opp.yolo_eval([y[b:b + 1] for y in ys], anchors, 3, a.classes, (a.size, a.size),
+                                score_threshold=SCORE, iou_threshold=IOU)
+        n += len(s)
+    return n
+
+
+def cpu_baseline(a, weights, anchors, budget_s=12.0):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    nimg = 4
+    x = make_inputs(a, nimg, 99)
+    oracle_step(weights, x, a, anchors)  # warm-up
+    t0 = time.perf_counter()
+    done = 0
+    while True:
+        oracle_step(weights, x, a, anchors)
+        done += nimg
+        el = time.perf_counter() - t0
+        if el > budget_s or done >= 64:
+            break
+    return {"value": done / el, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d images (%d passes of batch %d) of the same workload through oracle/ "
+                      "(torch-CPU restatement of the reference TF graph + numpy/C yolo_eval), %.1f s"
+                      % (done, done // nimg, nimg, el)}
+
+
+def run_reference(a):
+    """Reference arm: the reference's CPU implementation of the path.  The reference is pure Python
+    on TensorFlow/Keras, not installable here, so this is the oracle port."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    anchors = np.array(ANCHORS, np.float32).reshape(-1, 2)
+    _, weights = make_weights(a)
+    nimg = max(1, a.ref_images)
+    x = make_inputs(a, nimg, 1234)
+    for _ in range(max(1, min(a.warmup, 2))):
+        oracle_step(weights, x, a, anchors)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        oracle_step(weights, x, a, anchors)
+    el = time.perf_counter() - t0
+    v = a.steps * nimg / el
+    sample = "%d images per step (bounded sample of the batch-%d workload), oracle/ torch-CPU port" % (nimg, a.batch)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": el / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ---------------------------------------------------------------------------------------------
+def run_b200(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from yoloret_b200.yolo import YOLO
+    from yoloret_b200 import parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    anchors = np.array(ANCHORS, np.float32).reshape(-1, 2)
+    nd, weights = make_weights(a)
+
+    import tempfile
+    tmp = tempfile.mkdtemp(prefix="yr_bench_")
+    with open(os.path.join(tmp, "anchors.txt"), "w") as f:
+        f.write(", ".join("%d" % v for v in ANCHORS))
+    with open(os.path.join(tmp, "classes.txt"), "w") as f:
+        f.write("\n".join("class%d" % i for i in range(a.classes)) + "\n")
+    flags = {"backbone": a.model, "classes_path": os.path.join(tmp, "classes.txt"),
+             "anchors_path": os.path.join(tmp, "anchors.txt"), "input_size": (a.size, a.size), "score": SCORE,
+             "nms": IOU, "weights": weights, "batch": a.batch, "pw_variant": a.pw_variant, "quiet": True}
+    if a.micro:
+        flags["micro_batch"] = a.micro
+    yolo = YOLO(flags)
+    eng = yolo.engine
+    gather = parallel.DetectionGather(eng.pp, world, rank) if world > 1 else None
+
+    # rank-distinct synthetic images, pinned on the host for the e2e leg
+    x_host = make_inputs(a, a.batch, 1234 + rank).pin_memory()
+    eng.input.copy_(x_host, non_blocking=True)
+    eng.pp.set_image_shapes((a.size, a.size))
+    graph = eng.capture(SCORE, IOU)
+    launches_per_step = eng.launches_per_forward
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def device_step():
+        graph.replay()
+        if gather is not None:
+            gather.all_gather()
+
+    # ---- value: inputs resident in HBM -----------------------------------------------------
+    for _ in range(max(a.warmup, 3)):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        device_step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    n_det = int(eng.pp.out_count.sum().item())
+
+    # ---- e2e: public API, host buffers, H2D + D2H inside -------------------------------------
+    def e2e_step():
+        res = yolo.detect_batch(x_host, use_graph=True, unpack=False)
+        if gather is not None:
+            gather.all_gather()
+            if rank == 0:
+                gather.read()
+        return res
+
+    for _ in range(max(a.warmup, 3)):
+        e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms_e2e = max(f0.elapsed_time(f1), wall_ms)  # host-side waits count: take the longer clock
+    clocks = sampler.stop() if rank == 0 else None
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    total_images = a.batch * world * a.steps
+    value = total_images / (ms * 1e-3)
+    e2e_value = total_images / (ms_e2e * 1e-3)
+    h2d = x_host.numel() * x_host.element_size()
+    d2h = eng.pp.d2h_bytes() * (world if (gather is not None) else 1)
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "global_batch": a.batch * world, "micro_batch": eng.micro,
+                   "parallelism": "batch-sharded x%d, NCCL all-gather of packed detections" % world if world > 1
+                   else "single GPU", "weights": "seeded random init (head biases calibrated to ~1% boxes > 0.2)",
+                   "score_threshold": SCORE, "iou_threshold": IOU, "detections_per_step_rank0": n_det,
+                   "l2": "inputs larger than L2: fp32 batch = %.0f MB and one step moves ~%.1f GB of activations "
+                         "through a 126 MB L2, so nothing survives between timed iterations"
+                         % (h2d / 1e6, nd.totals()["bytes"] * a.batch / 1e9)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / a.steps, "api": "YOLO.detect_batch(pinned host fp32 [B,416,416,3])"},
+        "gpu_launches": launches_per_step * a.steps,
+        "clocks": clocks,
+    }
+
+    if rank == 0 and not a.no_roofline:
+        hbm, tf, which = measured_peaks()
+        prof = eng.profile_layers(SCORE, IOU, reps=3)
+        kinds = {}
+        for r in prof:
+            k = kinds.setdefault(r["kind"], {"ms": 0.0, "bytes": 0, "flops": 0, "launches": 0})
+            k["ms"] += r["ms"]
+            k["bytes"] += r["bytes"]
+            k["flops"] += r["flops"]
+            k["launches"] += r["launches"]
+        tot = sum(k["ms"] for k in kinds.values())
+        top = max(kinds, key=lambda k: kinds[k]["ms"])
+        K = kinds[top]
+        achieved = K["bytes"] / (K["ms"] * 1e-3) / 1e9
+        names = {"pw": "pw_simt_kernel / pw_tc_kernel (pointwise 1x1 conv)", "dw": "dw_kernel (depthwise conv)"}
+        out["roofline"] = {"bound": "hbm", "kernel": names.get(top, top), "achieved": achieved, "peak": hbm,
+                           "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "peak_source": which,
+                           "share_of_step": K["ms"] / tot, "launches_per_step": K["launches"],
+                           "algorithmic_bytes_per_step": K["bytes"], "tflops": K["flops"] / (K["ms"] * 1e-3) / 1e12}
+        out["kernels"] = {k: {"ms_per_step": round(v["ms"], 4), "share": round(v["ms"] / tot, 4),
+                              "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None,
+                              "launches": v["launches"]} for k, v in sorted(kinds.items(), key=lambda kv: -kv[1]["ms"])}
+        out["whole_net"] = {"algorithmic_GB_per_step": nd.totals()["bytes"] * a.batch / 1e9,
+                            "GBps_at_value": nd.totals()["bytes"] * a.batch / 1e9 / (ms / a.steps * 1e-3),
+                            "frac_of_hbm_peak": nd.totals()["bytes"] * a.batch / 1e9 / (ms / a.steps * 1e-3) / hbm}
+        if os.environ.get("YR_BENCH_LAYERS"):
+            with open(os.environ["YR_BENCH_LAYERS"], "w") as f:
+                json.dump(prof, f, indent=1)
+
+    if rank == 0 and not a.no_cpu_baseline and world == 1:
+        out["cpu_baseline"] = cpu_baseline(a, weights, anchors)
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

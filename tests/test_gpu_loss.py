@@ -31,6 +31,7 @@ def _make(B, hw, ncls, anchors, n_boxes, seed):
 @pytest.mark.parametrize("B,hw,ncls,n_boxes", [(2, (128, 128), 20, 6), (3, (96, 160), 80, 8), (2, (64, 64), 4, 0)])
 def test_loss_and_grad_match_oracle(built_lib, anchors, B, hw, ncls, n_boxes):
     yts, yos = _make(B, hw, ncls, anchors, n_boxes, seed=B)
+    exercised = 0
     for idx in range(3):
         ref_in = yos[idx].double().requires_grad_(True)
         ref, parts = oloss.yolo_loss_scale(yts[idx].double(), ref_in, idx, anchors)
@@ -42,12 +43,14 @@ def test_loss_and_grad_match_oracle(built_lib, anchors, B, hw, ncls, n_boxes):
         got_parts = L.last_parts.cpu().numpy()
         np.testing.assert_allclose(got_parts[:3], [float(p) for p in parts[:3]], rtol=2e-4, atol=1e-5)
         assert got_parts[3] == float(parts[3])  # sum(ignore_mask)
-        np.testing.assert_allclose(float(loss), float(ref), rtol=2e-4)
+        np.testing.assert_allclose(float(loss.detach()), float(ref.detach()), rtol=2e-4)
         gref = ref_in.grad.float().numpy()
         ggot = out.grad.cpu().numpy()
         np.testing.assert_allclose(ggot, gref, rtol=2e-3, atol=2e-6)
-        if n_boxes:
-            assert np.abs(gref[..., :4]).max() > 0  # the GIoU branch is exercised
+        if float(yts[idx][..., 4].sum()) > 0:  # this scale holds objects: the GIoU branch is exercised
+            assert np.abs(gref[..., :4]).max() > 0
+            exercised += 1
+    assert exercised > 0 or n_boxes == 0
 
 
 def test_functional_yolo_loss_sums_scales(built_lib, anchors):

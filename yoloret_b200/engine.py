@@ -261,3 +261,50 @@ class Engine:
 
     def results(self, with_float_boxes: bool = False):
         return self.pp.results(with_float_boxes)
+
+    # ---- per-layer timing (bench.py's roofline leg) ------------------------------------------
+    def profile_layers(self, score_threshold: float, iou_threshold: float, reps: int = 3):
+        """Times every launch of one full step with CUDA events on the launching stream, inside the
+        real pipeline order (so each layer sees the cache state it sees in production).  A spin
+        kernel ahead of each pass lets the host enqueue ahead of the device, so the event deltas are
+        kernel durations, not launch gaps.  Returns a list of dicts, one per layer kind + layer name:
+        ``{"kind", "name", "ms" (summed over micro-batches, averaged over reps), "bytes", "flops",
+        "launches"}`` for one step over the whole batch."""
+        st = self._stream()
+        net = self.net
+        n_layers = len(net.layers)
+        chunks = [(c0, min(self.micro, self.batch - c0)) for c0 in range(0, self.batch, self.micro)]
+        acc = np.zeros(n_layers + 3)
+        for _ in range(reps):
+            evs = []
+            torch.cuda._sleep(20_000_000)  # ~10 ms head start for the host
+            for c0, nb in chunks:
+                ops, cnt = self.build_plan(c0, nb)
+                row = [torch.cuda.Event(enable_timing=True) for _ in range(cnt + 1)]
+                row[0].record()
+                for i in range(cnt):
+                    _lib.check(self.lib.yr_run_ops(C.byref(ops[i]), 1, st), "yr_run_ops")
+                    row[i + 1].record()
+                evs.append(row)
+            pp_ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ptrs = [self.buf_t[v.buf.name].data_ptr() for v in net.outputs[:self.num_scales]]
+            ld = [v.buf.ld for v in net.outputs[:self.num_scales]]
+            self.pp.run(ptrs, ld, score_threshold, iou_threshold, st, events=pp_ev)
+            torch.cuda.synchronize(self.device)
+            for row in evs:
+                for i in range(n_layers):
+                    acc[i] += row[i].elapsed_time(row[i + 1])
+            for j in range(3):
+                acc[n_layers + j] += pp_ev[j].elapsed_time(pp_ev[j + 1])
+        acc /= reps
+        out = []
+        for i, L in enumerate(net.layers):
+            out.append(dict(kind=L.kind, name=L.name, ms=float(acc[i]), bytes=int(L.bytes_alg) * self.batch,
+                            flops=int(L.flops) * self.batch, launches=len(chunks)))
+        E = self.num_classes + 5
+        dec_bytes = self.batch * self.total_boxes * (E + 4) * 4
+        out.append(dict(kind="decode", name="decode_filter", ms=float(acc[n_layers]), bytes=dec_bytes, flops=0, launches=1))
+        out.append(dict(kind="nms", name="nms_classwise", ms=float(acc[n_layers + 1]), bytes=0, flops=0, launches=1))
+        out.append(dict(kind="pack", name="pack_detections", ms=float(acc[n_layers + 2]),
+                        bytes=self.pp.wire_words * 4, flops=0, launches=1))
+        return out

@@ -40,24 +40,43 @@ class PostProcess:
         self.cand_count = torch.zeros(B, Cn, dtype=i32, device=dev)
         self.det = torch.zeros(B, Cn, max_boxes, 6, dtype=f32, device=dev)
         self.det_count = torch.zeros(B, Cn, dtype=i32, device=dev)
-        self.status = torch.zeros(1, dtype=i32, device=dev)
         slots = Cn * max_boxes
-        self.out_boxes_f = torch.zeros(B, slots, 4, dtype=f32, device=dev)
-        self.out_boxes_i = torch.zeros(B, slots, 4, dtype=i32, device=dev)
-        self.out_scores = torch.zeros(B, slots, dtype=f32, device=dev)
-        self.out_classes = torch.zeros(B, slots, dtype=i32, device=dev)
-        self.out_count = torch.zeros(B, dtype=i32, device=dev)
+        # One flat int32 "wire" buffer holds everything a caller reads back, so a step's result is ONE
+        # device->host copy and (multi-GPU) ONE all-gather:  [count B | status 1 | pad | boxes_i B*slots*4 |
+        # scores B*slots | classes B*slots] and, behind the wire part, the un-truncated float boxes.
+        hdr = (B + 1 + 3) // 4 * 4
+        self.wire_words = hdr + B * slots * 6
+        self.flat = torch.zeros(self.wire_words + B * slots * 4, dtype=i32, device=dev)
+        o = 0
+        self.out_count = self.flat[o:o + B]
+        self.status = self.flat[B:B + 1]
+        o = hdr
+        self.out_boxes_i = self.flat[o:o + B * slots * 4].view(B, slots, 4)
+        o += B * slots * 4
+        self.out_scores = self.flat[o:o + B * slots].view(torch.float32).view(B, slots)
+        o += B * slots
+        self.out_classes = self.flat[o:o + B * slots].view(B, slots)
+        o += B * slots
+        self.out_boxes_f = self.flat[o:o + B * slots * 4].view(torch.float32).view(B, slots, 4)
+        self.wire = self.flat[:self.wire_words]
+        self._hdr, self._slots = hdr, slots
+        self.host_flat = torch.zeros(self.flat.numel(), dtype=i32).pin_memory()
         self.image_shapes = torch.zeros(B, 2, dtype=f32, device=dev)
+        self._shapes_host = None
         self.workspace_bytes = sum(t.numel() * t.element_size() for t in (
-            self.boxes, self.cand_score, self.cand_index, self.cand_count, self.det, self.det_count,
-            self.out_boxes_f, self.out_boxes_i, self.out_scores, self.out_classes, self.out_count))
+            self.boxes, self.cand_score, self.cand_index, self.cand_count, self.det, self.det_count, self.flat))
 
     def set_image_shapes(self, shapes):
         """shapes: [B,2] (h,w) of the original images (yolo_eval's image_shape), or one (h,w) for all."""
-        s = torch.as_tensor(np.asarray(shapes, dtype=np.float32))
-        if s.dim() == 1:
-            s = s[None].expand(self.batch, 2)
-        self.image_shapes.copy_(s.contiguous(), non_blocking=True)
+        a = np.asarray(shapes, dtype=np.float32)
+        if a.ndim == 1:
+            a = np.broadcast_to(a[None], (self.batch, 2))
+        if a.shape != (self.batch, 2):
+            raise ValueError("image_shapes must be [%d,2] or one (h,w), got %s" % (self.batch, a.shape))
+        if self._shapes_host is not None and np.array_equal(a, self._shapes_host):
+            return  # unchanged since the last call: nothing to upload
+        self._shapes_host = a.copy()
+        self.image_shapes.copy_(torch.from_numpy(self._shapes_host))
 
     def params(self, score_threshold: float, ld: Sequence[int]) -> YrDecodeParams:
         p = YrDecodeParams()
@@ -74,7 +93,7 @@ class PostProcess:
         return p
 
     def run(self, feat_ptrs: Sequence[int], ld: Sequence[int], score_threshold: float, iou_threshold: float,
-            stream: Optional[int] = None) -> int:
+            stream: Optional[int] = None, events=None) -> int:
         """decode+filter -> class-wise NMS -> pack.  Returns the number of kernels launched."""
         st = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
         p = self.params(score_threshold, ld)
@@ -82,33 +101,73 @@ class PostProcess:
         for s in range(self.num_scales):
             fp[s] = feat_ptrs[s]
         lib = self.lib
+        if events is not None:  # bench.py per-kernel timing: 4 events around the 3 launches
+            events[0].record()
         _lib.check(lib.yr_decode_filter(fp, self.image_shapes.data_ptr(), C.byref(p), self.boxes.data_ptr(),
                                         self.cand_score.data_ptr(), self.cand_index.data_ptr(),
                                         self.cand_count.data_ptr(), st), "yr_decode_filter")
+        if events is not None:
+            events[1].record()
         _lib.check(lib.yr_nms_classwise(self.boxes.data_ptr(), self.total_boxes, self.cand_score.data_ptr(),
                                         self.cand_index.data_ptr(), self.cand_count.data_ptr(), self.batch,
                                         self.num_classes, self.cand_cap, self.max_boxes, float(iou_threshold),
                                         self.det.data_ptr(), self.det_count.data_ptr(), self.status.data_ptr(), st),
                    "yr_nms_classwise")
+        if events is not None:
+            events[2].record()
         _lib.check(lib.yr_pack_detections(self.det.data_ptr(), self.det_count.data_ptr(), self.batch, self.num_classes,
                                           self.max_boxes, self.out_boxes_f.data_ptr(), self.out_boxes_i.data_ptr(),
                                           self.out_scores.data_ptr(), self.out_classes.data_ptr(),
                                           self.out_count.data_ptr(), st), "yr_pack_detections")
+        if events is not None:
+            events[3].record()
         return 3
 
-    def d2h_bytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in (self.out_boxes_i, self.out_scores, self.out_classes,
-                                                          self.out_count, self.status))
+    def d2h_bytes(self, with_float_boxes: bool = False) -> int:
+        return (self.flat.numel() if with_float_boxes else self.wire_words) * 4
 
-    def results(self, with_float_boxes: bool = False):
-        """Device->host read.  Per image: (boxes int32 [n,4] (ymin,xmin,ymax,xmax), scores f32 [n], classes int32 [n])."""
-        cnt = self.out_count.cpu().numpy()
-        bi, sc, cl = self.out_boxes_i.cpu().numpy(), self.out_scores.cpu().numpy(), self.out_classes.cpu().numpy()
-        bf = self.out_boxes_f.cpu().numpy() if with_float_boxes else None
-        if int(self.status.item()) != 0:
+    def read_wire(self, with_float_boxes: bool = False) -> np.ndarray:
+        """ONE device->host copy of the wire buffer into pinned host memory (synchronises the stream)."""
+        n = self.flat.numel() if with_float_boxes else self.wire_words
+        self.host_flat[:n].copy_(self.flat[:n], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self.host_flat[:n].numpy()
+
+    def unpack_wire(self, w: np.ndarray, with_float_boxes: bool = False):
+        """wire words (one rank's) -> per image (boxes int32 [n,4] (ymin,xmin,ymax,xmax), scores f32 [n],
+        classes int32 [n]) in yolo_eval order (class-major, NMS selection order within a class)."""
+        B, slots, hdr = self.batch, self._slots, self._hdr
+        if int(w[B]) != 0:
             raise _lib.YrError("candidate list overflow (cand_cap=%d): raise cand_cap" % self.cand_cap)
+        cnt = w[:B]
+        o = hdr
+        bi = w[o:o + B * slots * 4].reshape(B, slots, 4)
+        o += B * slots * 4
+        sc = w[o:o + B * slots].view(np.float32).reshape(B, slots)
+        o += B * slots
+        cl = w[o:o + B * slots].reshape(B, slots)
+        o += B * slots
+        bf = w[o:o + B * slots * 4].view(np.float32).reshape(B, slots, 4) if with_float_boxes else None
         out = []
-        for b, n in enumerate(cnt):
+        for b in range(B):
+            n = int(cnt[b])
             r = (bi[b, :n].copy(), sc[b, :n].copy(), cl[b, :n].copy())
             out.append(r + (bf[b, :n].copy(),) if with_float_boxes else r)
         return out
+
+    def padded_views(self, w: np.ndarray):
+        """wire words -> (counts [B], boxes int32 [B,slots,4], scores f32 [B,slots], classes int32 [B,slots])
+        numpy views (no copies); rows >= counts[b] are zero / class -1."""
+        B, slots, hdr = self.batch, self._slots, self._hdr
+        if int(w[B]) != 0:
+            raise _lib.YrError("candidate list overflow (cand_cap=%d): raise cand_cap" % self.cand_cap)
+        o = hdr
+        bi = w[o:o + B * slots * 4].reshape(B, slots, 4)
+        o += B * slots * 4
+        sc = w[o:o + B * slots].view(np.float32).reshape(B, slots)
+        o += B * slots
+        return w[:B], bi, sc, w[o:o + B * slots].reshape(B, slots)
+
+    def results(self, with_float_boxes: bool = False):
+        """Device->host read.  Per image: (boxes int32 [n,4] (ymin,xmin,ymax,xmax), scores f32 [n], classes int32 [n])."""
+        return self.unpack_wire(self.read_wire(with_float_boxes), with_float_boxes)

@@ -30,7 +30,8 @@ class YoloModel:
     """reference code/yolo.py:51.  ``model([bytes]) -> (boxes, scores, classes)``."""
 
     def __init__(self, model_body, num_anchors, num_scales, classes, model_path, anchors, input_shape, score=0.2,
-                 nms=0.5, with_classes=False, name=None, batch=1, weights=None, input_u8=False, **kwargs):
+                 nms=0.5, with_classes=False, name=None, batch=1, weights=None, input_u8=False, quiet=False,
+                 **kwargs):
         self.num_anchors, self.num_scales, self.classes = num_anchors, num_scales, classes
         self.with_classes, self.num_classes = with_classes, len(classes)
         self.model_path, self.anchors, self.score, self.nms = model_path, anchors, score, nms
@@ -45,7 +46,8 @@ class YoloModel:
         else:
             self.model.load_weights(self.model_path, anchors=anchors)
         self.engine = self.model.engine
-        print(self.model_path)
+        if not quiet:
+            print(self.model_path)
 
     def parse_image(self, image: bytes):
         """reference code/yolo.py:105-112: decode (host, PIL) -> letterbox on the GPU."""
@@ -83,6 +85,7 @@ class YOLO(object):
         self.nms = FLAGS.get('nms', 0.5)
         self.with_classes = FLAGS.get('with_classes', False)
         self.num_scales = FLAGS.get('num_scales', 3)
+        self.quiet = bool(FLAGS.get('quiet', False))  # engine extension: silence the reference's prints
         self.generate(FLAGS)
 
     def generate(self, FLAGS):
@@ -103,9 +106,11 @@ class YOLO(object):
         extra = {k: FLAGS[k] for k in ('micro_batch', 'device', 'pw_variant') if k in FLAGS}
         self.yolo_model = YoloModel(model_body, num_anchors, self.num_scales, self.class_names, model_path,
                                     self.anchors, self.input_shape, self.score, self.nms, self.with_classes,
-                                    batch=batch, weights=weights, input_u8=bool(FLAGS.get('input_u8', False)), **extra)
+                                    batch=batch, weights=weights, input_u8=bool(FLAGS.get('input_u8', False)),
+                                    quiet=self.quiet, **extra)
         self.engine = self.yolo_model.engine
-        print('{} model, anchors, and classes loaded.'.format(model_path))
+        if not self.quiet:
+            print('{} model, anchors, and classes loaded.'.format(model_path))
         hsv_tuples = [(x / len(self.class_names), 1., 1.) for x in range(len(self.class_names))]
         self.colors = list(map(lambda x: colorsys.hsv_to_rgb(*x), hsv_tuples))
         self.colors = list(map(lambda x: (int(x[0] * 255), int(x[1] * 255), int(x[2] * 255)), self.colors))
@@ -123,7 +128,8 @@ class YOLO(object):
         start = timer()
         out_boxes, out_scores, out_classes = self.yolo_model([image_data])
         end = timer()
-        print('Found {} boxes for {}'.format(len(out_boxes), 'img'))
+        if not self.quiet:
+            print('Found {} boxes for {}'.format(len(out_boxes), 'img'))
         if not draw:
             return out_boxes, out_scores, out_classes
         from PIL import Image, ImageDraw, ImageFont
@@ -143,16 +149,19 @@ class YOLO(object):
             for t in range(thickness):
                 d.rectangle([left + t, top + t, right - t, bottom - t], outline=self.colors[c])
             d.text((left, max(0, top - 10)), label, fill=self.colors[c], font=font)
-        print(end - start)
+        if not self.quiet:
+            print(end - start)
         return img
 
     # ---- batched extension -----------------------------------------------------------
-    def detect_batch(self, images, image_shapes=None, use_graph: bool = True):
+    def detect_batch(self, images, image_shapes=None, use_graph: bool = True, unpack: bool = True):
         """``images``: [B,H,W,3] tensor already at the network input size - uint8 (scaled by 1/255
         on the GPU like tf.io.decode_image(dtype=float32)) or float32 in [0,1] - on the host
         (pinned memory recommended) or on the device.  ``image_shapes``: [B,2] original (h,w)
         per image (default: the input size).  Returns per-image (boxes, scores, classes) numpy
-        arrays; includes the host->device copy of the batch and the device->host read of results."""
+        arrays (``unpack=False``: the padded form ``(counts [B], boxes [B,20*C,4] int32, scores
+        [B,20*C], classes [B,20*C])`` as views of the pinned host buffer, valid until the next call);
+        includes the host->device copy of the batch and ONE device->host read of the results."""
         e = self.engine
         if tuple(images.shape) != tuple(e.input.shape) or images.dtype != e.input.dtype:
             raise ValueError("expected %s %s, got %s %s" % (tuple(e.input.shape), e.input.dtype,
@@ -165,4 +174,6 @@ class YOLO(object):
             self._graph.replay()
         else:
             e.step(self.score, self.nms)
-        return e.results()
+        if unpack:
+            return e.results()
+        return e.pp.padded_views(e.pp.read_wire())
