@@ -95,7 +95,8 @@ typedef struct yr_op {
     int32_t k, stride, pad_t, pad_l;
     int32_t ld_in, ld_in2, ld_in3, ld_in4, ld_out, ld_res;
     int32_t K2, K3, K4;      /* RFCR: channels of in2..in4 */
-    int32_t variant;         /* PW kernel choice: 0 = auto, 1 = SIMT fp32, 2 = tcgen05 3xTF32 */
+    int32_t variant;         /* PW kernel choice: 0 = auto (tcgen05 when w_tc is given), 1 = SIMT fp32,
+                                2 = tcgen05 3xTF32 */
     const void* in;
     const void* in2;
     const void* in3;
@@ -105,6 +106,7 @@ typedef struct yr_op {
     const float* bias;
     const float* res;
     const float* scale;
+    const float* w_tc;       /* PW: weight image made by yr_pw_tc_pack (tensor-core variant), or NULL */
 } yr_op;
 
 /* Library identity / errors. */
@@ -116,6 +118,15 @@ int yr_sizeof_op(void); /* sizeof(yr_op), for binding self-checks */
  * (reference yolov3_body, code/yolo3/model.py:170-342, called from
  * YoloModel.call code/yolo.py:152) is one call of this. */
 int yr_run_ops(const yr_op* ops, int n_ops, void* stream);
+
+/* Tensor-core pointwise variant: the 1x1 kernel W [K][N] (row-major, BN scale folded, the same
+ * array yr_op.w points to) is split into TF32 (hi, lo) halves and stored in the swizzled
+ * shared-memory image the tcgen05 kernel bulk-copies.  Done once per layer at weight-load time
+ * (replaces model.load_weights for these layers, reference code/yolo.py:87).
+ *   yr_pw_tc_packed_floats  number of floats `packed` must hold (0 = shape unsupported)
+ *   yr_pw_tc_pack           packed must be 128-byte aligned */
+int64_t yr_pw_tc_packed_floats(int K, int N);
+int yr_pw_tc_pack(const float* w, int K, int N, float* packed, void* stream);
 
 /* ---- post-process: yolo_eval (reference code/yolo3/model.py:431-491) --------- */
 

@@ -30,8 +30,14 @@ def _rand(*shape, seed=0, scale=1.0):
     (2, 5, 5, 96, 144, 96, "swish", True, True),
     (1, 3, 3, 720, 120, 720, "none", True, False),
     (2, 9, 9, 48, 96, 48, "relu6", False, False),
+    (2, 40, 40, 16, 96, 16, "relu6", False, False),     # K < one k-block, many M tiles (weights stay resident)
+    (1, 30, 30, 120, 720, 120, "relu6", False, False),  # N > 256: three n tiles
+    (3, 13, 13, 512, 512, 512, "relu6", False, False),  # streamed weights, two n tiles
+    (2, 64, 64, 256, 256, 256, "none", True, False),    # widest single n tile, > 1 tile per CTA? (64 tiles)
+    (4, 100, 100, 24, 144, 24, "relu6", False, False),  # 313 tiles > 148 CTAs: persistent loop, both accumulators
 ])
-def test_pw_parity(built_lib, B, H, W, K, N, ld_in, act, use_res, use_scale):
+@pytest.mark.parametrize("variant", [1, 2])
+def test_pw_parity(built_lib, B, H, W, K, N, ld_in, act, use_res, use_scale, variant):
     a = _rand(B, H, W, ld_in, seed=1)
     w = _rand(K, N, seed=2, scale=K ** -0.5)
     bias = _rand(N, seed=3)
@@ -44,7 +50,7 @@ def test_pw_parity(built_lib, B, H, W, K, N, ld_in, act, use_res, use_scale):
     if use_res:
         ref = ref + res.double()
     out = pw_op(a.cuda(), w.cuda(), bias.cuda(), act, res.cuda() if use_res else None,
-                scale.cuda() if use_scale else None, ld_out=N + 8)
+                scale.cuda() if use_scale else None, ld_out=N + 8, variant=variant)
     got = out[..., :N].cpu().double()
     assert torch.isnan(out[..., N:]).all(), "kernel wrote outside its channel slice"
     torch.testing.assert_close(got, ref, rtol=RTOL, atol=ATOL)

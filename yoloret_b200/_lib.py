@@ -32,6 +32,7 @@ class YrOp(C.Structure):
         ("in_", C.c_void_p), ("in2", C.c_void_p), ("in3", C.c_void_p), ("in4", C.c_void_p),
         ("out", C.c_void_p),
         ("w", C.c_void_p), ("bias", C.c_void_p), ("res", C.c_void_p), ("scale", C.c_void_p),
+        ("w_tc", C.c_void_p),
     ]
 
 
@@ -62,6 +63,8 @@ SYMBOLS = {
     "yr_last_error": (C.c_char_p, []),
     "yr_sizeof_op": (C.c_int, []),
     "yr_run_ops": (C.c_int, [C.POINTER(YrOp), C.c_int, _P]),
+    "yr_pw_tc_packed_floats": (C.c_int64, [C.c_int, C.c_int]),
+    "yr_pw_tc_pack": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "yr_decode_filter": (C.c_int, [C.POINTER(_P), _P, C.POINTER(YrDecodeParams), _P, _P, _P, _P, _P]),
     "yr_nms_classwise": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                    _P, _P, _P, _P]),

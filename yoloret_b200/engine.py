@@ -120,12 +120,15 @@ class Engine:
     def _prep_weights(self, w):
         """Folds BN, pads channels to the device layout and uploads."""
         self.wdev: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self.wtc: Dict[int, torch.Tensor] = {}   # tensor-core weight images of the pointwise layers
         for i, L in enumerate(self.net.layers):
             if L.kind == "pw":
                 k = w[L.conv + "/kernel"][0, 0].astype(np.float64)          # [Cin, Cout]
                 s, b = _fold_bn(w, L.bn, k.shape[1])
                 mat = _pad_cols(_expand_rows(k * s[None, :], L.inp[0].segs), L.out.C)
                 self.wdev[i] = (self._dev(mat), self._dev(_pad_cols(b, L.out.C)))
+                if self.pw_variant != _lib.PW_SIMT:
+                    self.wtc[i] = self._pack_tc(self.wdev[i][0])
             elif L.kind == "dw":
                 k = w[L.conv + "/depthwise_kernel"][:, :, :, 0].astype(np.float64)  # [k,k,C]
                 s, b = _fold_bn(w, L.bn, k.shape[2])
@@ -149,7 +152,20 @@ class Engine:
                         for cn, v in zip(L.extra["convs"], L.inp)]
                 mat = _pad_cols(np.concatenate(mats, 0), L.out.C)
                 self.wdev[i] = (self._dev(mat), self._dev(w["weighted_sum/alpha"]))
+        torch.cuda.synchronize(self.device)
         self.weight_bytes = sum(a.numel() * 4 + b.numel() * 4 for a, b in self.wdev.values())
+
+    def _pack_tc(self, w_kn: torch.Tensor) -> Optional[torch.Tensor]:
+        """yr_pw_tc_pack: [K,N] fp32 -> split/swizzled TF32 (hi, lo) image for the tcgen05 kernel."""
+        K, N = int(w_kn.shape[0]), int(w_kn.shape[1])
+        n = int(self.lib.yr_pw_tc_packed_floats(K, N))
+        if n <= 0:
+            if self.pw_variant == _lib.PW_TC:
+                raise _lib.YrError("no tensor-core tiling for a %dx%d pointwise layer" % (K, N))
+            return None  # auto: this layer stays on the exact-fp32 SIMT kernel
+        packed = torch.empty(n, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.yr_pw_tc_pack(w_kn.data_ptr(), K, N, packed.data_ptr(), self._stream()), "yr_pw_tc_pack")
+        return packed
 
     # ---- plan ---------------------------------------------------------------------
     def _ptr(self, v: View, chunk0: int) -> int:
@@ -187,6 +203,8 @@ class Engine:
             elif L.kind == "pw":
                 o.kind = _lib.OP_PW
                 o.variant = self.pw_variant
+                if self.wtc.get(i) is not None:
+                    o.w_tc = self.wtc[i].data_ptr()
                 if L.res is not None:
                     o.res, o.ld_res = self._ptr(L.res, chunk0), L.res.buf.ld
                 if L.gate is not None:
