@@ -32,7 +32,7 @@ constexpr int BM = 128;                      // rows per tile = UMMA M
 constexpr int BK = 32;                       // fp32 per k-block = one 128-byte swizzle row
 constexpr int A_TILE_BYTES = BM * BK * 4;    // 16 KB (raw/hi) ; lo tile has the same size
 constexpr int NUM_THREADS = 320;
-constexpr int EPI_LD = 33;                   // padded row of the per-warp transpose buffer
+constexpr int EPI_LD = 36;                   // padded row (floats) of the per-warp transpose buffer
 constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
 constexpr int SMEM_LIMIT = 232448;           // 227 KB per CTA
 constexpr int MAX_A_STAGES = 8, MAX_B_SLOTS = 24;
@@ -63,20 +63,21 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
+    // the suspend-time hint lets the hardware park the warp until the phase completes (it wakes
+    // on the arrival, ~60 cycles), so idle roles do not steal issue slots from working ones
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(0x989680u)
         : "memory");
     return ok != 0;
 }
 // Bounded wait: a protocol bug traps (and fails the launch loudly) instead of hanging the GPU.
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int what) {
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 8000000000LL) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+        if (spins > (1u << 24)) {
             printf("yoloret_b200 pw_tc: mbarrier wait timed out (role %d, block %d, thread %d)\n", what, blockIdx.x,
                    threadIdx.x);
             __trap();
@@ -138,10 +139,77 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
     return d;
 }
 
-__device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
+// fp32 -> TF32 (10-bit mantissa), round to nearest / ties away == cvt.rna.tf32.f32, but on the integer
+// ALU: the conversion instruction runs on the quarter-rate XU pipe and the converter warps do 64 per tile row.
+__host__ __device__ __forceinline__ float tf32_rna(float x) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+#else
+    union { float f; uint32_t u; } v;
+    v.f = x;
+    v.u = (v.u + 0x1000u) & 0xFFFFE000u;
+    return v.f;
+#endif
+}
+
+// ---- epilogue: TMEM -> registers -> smem transpose -> bias / activation / residual -> 128-bit row stores
+// One warp owns TMEM lane quarter q (32 tile rows).  Per 32-column chunk: the accumulator row a lane
+// holds goes to smem as 8 STS.128 (row stride 36 floats: conflict-free per 8-lane phase), comes back
+// as LDS.128 with 8 lanes covering one row, and leaves as STG.128: 4 full 128-byte lines per store.
+constexpr int ACC_FULL_IDX = 3 * MAX_A_STAGES + 2 * MAX_B_SLOTS;
+
+template <int ACT, bool HAS_RES>
+__device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, uint32_t tmem_base, uint32_t bar0, int item0,
+                                              int item1, int q, int lane) {
+    const int sub_r = lane >> 3;        // row within a 4-row group
+    const int sub_c = (lane & 7) << 2;  // first of this lane's 4 columns within the chunk
+    uint32_t it = 0;
+    for (int item = item0; item < item1; ++item, ++it) {
+        const int nt = item / p.m_tiles, mt = item - nt * p.m_tiles;
+        const uint32_t acc = it & 1;
+        mbar_wait(bar0 + 8u * (ACC_FULL_IDX + acc), (it >> 1) & 1, 6);
+        tc_fence_after();
+        const int row0 = mt * BM + q * 32;
+        const int ncols = min(p.BN, p.N - nt * p.BN);  // valid columns of this n tile (multiple of 8)
+        const int rows = min(32, p.M - row0);          // valid rows of this warp's slab (may be <= 0)
+        const uint32_t tsrc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.acc_stride;
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+            float v[32];
+            tmem_ld32(tsrc + c0, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(stg + lane * EPI_LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            __syncwarp();
+            const int c = c0 + sub_c;
+            if (c < ncols) {
+                const int n = nt * p.BN + c;
+                const float4 bv = ldg4(p.bias + n);
+                float* op = p.out + (size_t)(row0 + sub_r) * p.ld_out + n;
+                const float* rp = HAS_RES ? p.res + (size_t)(row0 + sub_r) * p.ld_res + n : nullptr;
+                const float* sp = stg + sub_r * EPI_LD + sub_c;
+                const size_t ostep = (size_t)4 * p.ld_out, rstep = (size_t)4 * p.ld_res;
+#pragma unroll 4
+                for (int r = sub_r; r < rows; r += 4) {
+                    float4 x = *reinterpret_cast<const float4*>(sp);
+                    x.x = apply_act<ACT>(x.x + bv.x);
+                    x.y = apply_act<ACT>(x.y + bv.y);
+                    x.z = apply_act<ACT>(x.z + bv.z);
+                    x.w = apply_act<ACT>(x.w + bv.w);
+                    if (HAS_RES) {
+                        const float4 rv = ldg4(rp);
+                        x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w;
+                        rp += rstep;
+                    }
+                    st4(op, x);
+                    op += ostep;
+                    sp += 4 * EPI_LD;
+                }
+            }
+            __syncwarp();
+        }
+        tc_fence_before();
+        mbar_arrive(bar0 + 8u * (ACC_FULL_IDX + 2 + acc));
+    }
 }
 
 // ---- the GEMM ------------------------------------------------------------------------------
@@ -302,38 +370,20 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
         }
     } else {
         // ===== epilogue =====
-        const int q = warp & 3;  // TMEM lane quarter this warp may access
         float* stg = reinterpret_cast<float*>(gbase + epi_off) + (warp - 6) * 32 * EPI_LD;
-        uint32_t it = 0;
-        for (int item = item0; item < item1; ++item, ++it) {
-            const int nt = item / p.m_tiles, mt = item - nt * p.m_tiles;
-            const uint32_t acc = it & 1;
-            mbar_wait(acc_full(acc), (it >> 1) & 1, 6);
-            tc_fence_after();
-            const int row0 = mt * BM + q * 32;
-            const int ncols = min(p.BN, p.N - nt * p.BN);  // valid columns of this n tile
-            for (int c0 = 0; c0 < ncols; c0 += 32) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.acc_stride + c0, v);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) stg[lane * EPI_LD + j] = v[j];
-                __syncwarp();
-                const int n = nt * p.BN + c0 + lane;
-                const bool ncol_ok = (c0 + lane) < ncols;
-                const float bv = ncol_ok ? __ldg(p.bias + n) : 0.f;
-                const int rmax = min(32, p.M - row0);
-                for (int r = 0; r < rmax; ++r) {
-                    float x = apply_act_rt(stg[r * EPI_LD + lane] + bv, p.act);
-                    if (ncol_ok) {
-                        const size_t row = (size_t)(row0 + r);
-                        if (p.res != nullptr) x += __ldg(p.res + row * p.ld_res + n);
-                        p.out[row * p.ld_out + n] = x;
-                    }
-                }
-                __syncwarp();
-            }
-            tc_fence_before();
-            mbar_arrive(acc_empty(acc));
+        const bool has_res = p.res != nullptr;
+        switch (p.act) {
+            case YR_ACT_RELU6:
+                if (has_res) epilogue_loop<YR_ACT_RELU6, true>(p, stg, tmem_base, bar0, item0, item1, warp & 3, lane);
+                else epilogue_loop<YR_ACT_RELU6, false>(p, stg, tmem_base, bar0, item0, item1, warp & 3, lane);
+                break;
+            case YR_ACT_SWISH:
+                if (has_res) epilogue_loop<YR_ACT_SWISH, true>(p, stg, tmem_base, bar0, item0, item1, warp & 3, lane);
+                else epilogue_loop<YR_ACT_SWISH, false>(p, stg, tmem_base, bar0, item0, item1, warp & 3, lane);
+                break;
+            default:
+                if (has_res) epilogue_loop<YR_ACT_NONE, true>(p, stg, tmem_base, bar0, item0, item1, warp & 3, lane);
+                else epilogue_loop<YR_ACT_NONE, false>(p, stg, tmem_base, bar0, item0, item1, warp & 3, lane);
         }
     }
 
@@ -447,11 +497,11 @@ int launch_pw_tc(const yr_op& op, cudaStream_t s) {
     YR_CHECK_ARG(op.in && op.out && op.w_tc && op.bias, "pw_tc: null pointer (w_tc = yr_pw_tc_pack output)");
     YR_CHECK_ARG(op.C > 0 && op.C % 8 == 0 && op.N > 0 && op.N % 8 == 0, "pw_tc: K=%d N=%d must be multiples of 8", op.C,
                  op.N);
-    YR_CHECK_ARG(op.ld_in >= op.C && op.ld_in % 4 == 0 && op.ld_out >= op.N, "pw_tc: bad ld_in=%d ld_out=%d", op.ld_in,
-                 op.ld_out);
-    YR_CHECK_ARG(!op.res || op.ld_res >= op.N, "pw_tc: bad ld_res=%d", op.ld_res);
-    YR_CHECK_ARG(((uintptr_t)op.in | (uintptr_t)op.w_tc | (uintptr_t)op.scale) % 16 == 0,
-                 "pw_tc: in / w_tc / scale must be 16-byte aligned");
+    YR_CHECK_ARG(op.ld_in >= op.C && op.ld_in % 4 == 0 && op.ld_out >= op.N && op.ld_out % 4 == 0,
+                 "pw_tc: bad ld_in=%d ld_out=%d", op.ld_in, op.ld_out);
+    YR_CHECK_ARG(!op.res || (op.ld_res >= op.N && op.ld_res % 4 == 0), "pw_tc: bad ld_res=%d", op.ld_res);
+    YR_CHECK_ARG(((uintptr_t)op.in | (uintptr_t)op.out | (uintptr_t)op.w_tc | (uintptr_t)op.bias | (uintptr_t)op.res |
+                  (uintptr_t)op.scale) % 16 == 0, "pw_tc: pointers must be 16-byte aligned");
     const long long M = (long long)op.B * op.H * op.W;
     YR_CHECK_ARG(M > 0 && M < (1ll << 31) - 256, "pw_tc: bad row count");
     tc::Tiling t;
