@@ -156,6 +156,14 @@ typedef struct yr_decode_params {
 int yr_decode_filter(const float* const feats[3], const float* image_shapes, const yr_decode_params* p,
                      float* boxes, float* cand_score, int32_t* cand_index, int32_t* cand_count, void* stream);
 
+/* yolo_head (model.py:344-371) as a standalone op of the public call surface.
+ *   feats [B,gh,gw,ld] raw logits (cell layout (anchor, 5+C)), anchors_dev [A][2] (w,h px) on the device
+ *   box_xy / box_wh [B,gh,gw,A,2], box_confidence [B,gh,gw,A,1], box_class_probs [B,gh,gw,A,C] (NULL when the
+ *   caller wants calc_loss=True outputs), grid [gh,gw,1,2] (x,y) or NULL. */
+int yr_yolo_head(const float* feats, int ld, int B, int gh, int gw, int A, int C, const float* anchors_dev,
+                 int input_h, int input_w, float* box_xy, float* box_wh, float* box_confidence,
+                 float* box_class_probs, float* grid, void* stream);
+
 /* Class-wise greedy NMS == the `for c in range(num_classes):
  * tf.image.non_max_suppression(...)` loop of model.py:474-486, bit-exact
  * selection (score desc, ties -> lower index; IoU > thr strict; TF IoU formula).

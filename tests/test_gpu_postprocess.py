@@ -171,3 +171,18 @@ def test_letterbox_parity(built_lib, ih, iw, size):
     ref = olb.letterbox_image(olb.u8_to_float(img), size)
     got = letterbox_image(torch.from_numpy(img).cuda(), size).cpu().numpy()
     np.testing.assert_allclose(got, ref, rtol=0, atol=2e-6)
+
+
+def test_yolo_head_matches_oracle(built_lib, anchors):
+    """Public yolo_head (reference model.py:344): all four outputs + the calc_loss=True form."""
+    from yoloret_b200.yolo3.model import yolo_head
+    rng = np.random.default_rng(3)
+    feats = rng.standard_normal((2, 5, 7, 3, 11)).astype(np.float32) * 2
+    anc = anchors[[3, 4, 5]]
+    ref = opp.yolo_head(feats, anc, (160, 224))
+    got = yolo_head(torch.from_numpy(feats).cuda(), anc, (160, 224))
+    for g, r in zip(got, ref):
+        np.testing.assert_allclose(g.cpu().numpy(), np.asarray(r).reshape(g.shape), rtol=2e-6, atol=1e-7)
+    grid, xy, wh, conf = yolo_head(torch.from_numpy(feats).cuda(), anc, (160, 224), calc_loss=True)
+    assert grid.shape == (5, 7, 1, 2) and float(grid[4, 6, 0, 0]) == 6.0 and float(grid[4, 6, 0, 1]) == 4.0
+    np.testing.assert_allclose(xy.cpu().numpy(), np.asarray(ref[0]).reshape(xy.shape), rtol=2e-6, atol=1e-7)

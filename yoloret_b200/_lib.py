@@ -66,6 +66,8 @@ SYMBOLS = {
     "yr_pw_tc_packed_floats": (C.c_int64, [C.c_int, C.c_int]),
     "yr_pw_tc_pack": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "yr_decode_filter": (C.c_int, [C.POINTER(_P), _P, C.POINTER(YrDecodeParams), _P, _P, _P, _P, _P]),
+    "yr_yolo_head": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int,
+                               _P, _P, _P, _P, _P, _P]),
     "yr_nms_classwise": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                    _P, _P, _P, _P]),
     "yr_pack_detections": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),

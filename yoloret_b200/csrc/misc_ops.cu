@@ -59,12 +59,92 @@ stem_kernel(const void* __restrict__ in_, const float* __restrict__ wgt, const f
     st4(out + (size_t)p * ld_out + n, v);
 }
 
+// v2: one thread owns CPT consecutive output channels of one output pixel, so the 27 input taps are
+// loaded once and reused CPT times from registers; weights are shared-memory broadcasts (all lanes of
+// a warp with the same channel slice read the same address).  FFMA-bound at ~the HBM time of the layer.
+template <int ACT, bool U8, int CPT>
+__global__ void __launch_bounds__(256)
+stem_kernel_v2(const void* __restrict__ in_, const float* __restrict__ wgt, const float* __restrict__ bias,
+               float* __restrict__ out, int ld_out, int B, int H, int W, int Ho, int Wo, int N, int stride, int pad_t,
+               int pad_l) {
+    extern __shared__ __align__(16) float sw[];  // [27][N]
+    for (int i = threadIdx.x; i < 27 * N; i += blockDim.x) sw[i] = wgt[i];
+    __syncthreads();
+    const int groups = N / CPT;
+    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * Ho * Wo * groups;
+    if (item >= total) return;
+    const int n = (int)(item % groups) * CPT;
+    const long long p = item / groups;
+    const int wo = (int)(p % Wo);
+    const int ho = (int)((p / Wo) % Ho);
+    const int b = (int)(p / ((long long)Wo * Ho));
+    float x[27];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+        const int hi = ho * stride - pad_t + kh;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+            const int wi = wo * stride - pad_l + kw;
+            const bool ok = hi >= 0 && hi < H && wi >= 0 && wi < W;
+            const size_t off = (((size_t)b * H + (ok ? hi : 0)) * W + (ok ? wi : 0)) * 3;
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+                float v;
+                if (U8) v = (float)__ldg(reinterpret_cast<const uint8_t*>(in_) + off + ci) * (1.0f / 255.0f);
+                else v = __ldg(reinterpret_cast<const float*>(in_) + off + ci);
+                x[(kh * 3 + kw) * 3 + ci] = ok ? v : 0.0f;
+            }
+        }
+    }
+    float acc[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) acc[j] = 0.0f;
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+#pragma unroll
+        for (int j4 = 0; j4 < CPT / 4; ++j4) {
+            const float4 wv = *reinterpret_cast<const float4*>(sw + t * N + n + j4 * 4);
+            acc[j4 * 4 + 0] = fmaf(x[t], wv.x, acc[j4 * 4 + 0]);
+            acc[j4 * 4 + 1] = fmaf(x[t], wv.y, acc[j4 * 4 + 1]);
+            acc[j4 * 4 + 2] = fmaf(x[t], wv.z, acc[j4 * 4 + 2]);
+            acc[j4 * 4 + 3] = fmaf(x[t], wv.w, acc[j4 * 4 + 3]);
+        }
+    }
+    float* o = out + (size_t)p * ld_out + n;
+#pragma unroll
+    for (int j4 = 0; j4 < CPT / 4; ++j4) {
+        const float4 bv = ldg4(bias + n + j4 * 4);
+        float4 v;
+        v.x = apply_act<ACT>(acc[j4 * 4 + 0] + bv.x);
+        v.y = apply_act<ACT>(acc[j4 * 4 + 1] + bv.y);
+        v.z = apply_act<ACT>(acc[j4 * 4 + 2] + bv.z);
+        v.w = apply_act<ACT>(acc[j4 * 4 + 3] + bv.w);
+        st4(o + j4 * 4, v);
+    }
+}
+
+template <int ACT, bool U8, int CPT>
+static void launch_stem_v2(const yr_op& op, cudaStream_t s) {
+    const long long total = (long long)op.B * op.Ho * op.Wo * (op.N / CPT);
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    const size_t smem = (size_t)27 * op.N * sizeof(float);
+    stem_kernel_v2<ACT, U8, CPT><<<grid, 256, smem, s>>>(op.in, op.w, op.bias, (float*)op.out, op.ld_out, op.B, op.H, op.W,
+                                                          op.Ho, op.Wo, op.N, op.stride, op.pad_t, op.pad_l);
+}
+
 template <int ACT>
 static int launch_stem_act(const yr_op& op, cudaStream_t s) {
     const long long total = (long long)op.B * op.Ho * op.Wo * (op.N / 4);
     const unsigned grid = (unsigned)((total + 255) / 256);
     const size_t smem = (size_t)27 * op.N * sizeof(float);
-    if (op.in_is_u8)
+    if (op.N % 12 == 0) {
+        if (op.in_is_u8) launch_stem_v2<ACT, true, 12>(op, s);
+        else launch_stem_v2<ACT, false, 12>(op, s);
+    } else if (op.N % 8 == 0) {
+        if (op.in_is_u8) launch_stem_v2<ACT, true, 8>(op, s);
+        else launch_stem_v2<ACT, false, 8>(op, s);
+    } else if (op.in_is_u8)
         stem_kernel<ACT, true><<<grid, 256, smem, s>>>(op.in, op.w, op.bias, (float*)op.out, op.ld_out, op.B, op.H, op.W,
                                                        op.Ho, op.Wo, op.N, op.stride, op.pad_t, op.pad_l);
     else

@@ -101,6 +101,109 @@ decode_filter_kernel(DecodeArgs a, const float* __restrict__ image_shapes, float
     }
 }
 
+// Sparse variant for score_threshold > 0 (the YOLO default is 0.2): score = conf * cls <= conf, so an
+// anchor whose objectness fails the threshold cannot produce a candidate and its C class logits are
+// never touched.  One warp per grid cell: the cell's A*(5+C) logits are one contiguous, 16-byte
+// aligned run, read with 128-bit loads; candidates are appended with one atomic each (their order
+// within a list is irrelevant: NMS orders by (score, index)).  Same arithmetic, op for op, as
+// decode_filter_kernel - only the work distribution differs.
+__global__ void __launch_bounds__(256)
+decode_sparse_kernel(DecodeArgs a, const float* __restrict__ image_shapes, float* __restrict__ boxes,
+                     float* __restrict__ cand_score, int32_t* __restrict__ cand_index, int32_t* __restrict__ cand_count,
+                     int total_cells) {
+    const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    if (warp_global >= total_cells) return;
+    const int C = a.C, E = C + 5;
+    int s = 0, cell = warp_global, cell_off = 0;
+    const int n0 = a.gh[0] * a.gw[0], n1 = a.num_scales > 1 ? a.gh[1] * a.gw[1] : 0;
+    if (a.num_scales > 1 && cell >= n0) { s = 1; cell -= n0; cell_off = n0; }
+    if (a.num_scales > 2 && s == 1 && cell >= n1) { s = 2; cell -= n1; cell_off = n0 + n1; }
+    (void)cell_off;
+    const float* f = a.feats[s] + ((size_t)b * a.gh[s] * a.gw[s] + cell) * a.ld[s];
+    // objectness of the 3 anchors
+    float conf = 0.0f;
+    if (lane < 3) conf = sigmoid_exact(__ldg(f + lane * E + 4));
+    const unsigned mask = __ballot_sync(0xffffffffu, lane < 3 && conf > a.thr);
+    if (mask == 0u) return;
+    const float c0 = __shfl_sync(0xffffffffu, conf, 0), c1 = __shfl_sync(0xffffffffu, conf, 1);
+    const float c2 = __shfl_sync(0xffffffffu, conf, 2);
+    const int box_base = a.box_off[s] + cell * 3;
+    if (lane < 3 && ((mask >> lane) & 1u)) {
+        const float img_h = __ldg(image_shapes + 2 * b), img_w = __ldg(image_shapes + 2 * b + 1);
+        const float max_shape = fmaxf(img_h, img_w);
+        const float boxed_h = a.in_h * (img_h / max_shape), boxed_w = a.in_w * (img_w / max_shape);
+        const float off_h = (a.in_h - boxed_h) / 2.0f, off_w = (a.in_w - boxed_w) / 2.0f;
+        const float scale_h = img_h / boxed_h, scale_w = img_w / boxed_w;
+        const int gx = cell % a.gw[s], gy = cell / a.gw[s];
+        const float* t = f + lane * E;
+        const float tx = __ldg(t), ty = __ldg(t + 1), tw = __ldg(t + 2), th = __ldg(t + 3);
+        const float bx = (sigmoid_exact(tx) + (float)gx) / (float)a.gw[s];
+        const float by = (sigmoid_exact(ty) + (float)gy) / (float)a.gh[s];
+        const float bw = expf(tw) * a.anchors[s][lane][0] / a.in_w;
+        const float bh = expf(th) * a.anchors[s][lane][1] / a.in_h;
+        const float y = (by * a.in_h - off_h) * scale_h;
+        const float x = (bx * a.in_w - off_w) * scale_w;
+        const float hh = bh * (a.in_h * scale_h);
+        const float ww = bw * (a.in_w * scale_w);
+        float4 o;
+        o.x = fminf(fmaxf(y - hh / 2.0f, 0.0f), img_h);
+        o.y = fminf(fmaxf(x - ww / 2.0f, 0.0f), img_w);
+        o.z = fminf(fmaxf(y + hh / 2.0f, 0.0f), img_h);
+        o.w = fminf(fmaxf(x + ww / 2.0f, 0.0f), img_w);
+        *reinterpret_cast<float4*>(boxes + ((size_t)b * a.total_boxes + box_base + lane) * 4) = o;
+    }
+    // class scores of the surviving anchors
+    const int valid = 3 * E;
+    for (int e0 = lane * 4; e0 < valid; e0 += 128) {
+        const float4 v4 = ldg4(f + e0);  // in bounds: ld >= 3E and ld % 4 == 0
+        const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int e = e0 + j;
+            if (e >= valid) break;
+            const int an = (e >= E) + (e >= 2 * E);
+            const int fld = e - an * E;
+            if (fld < 5 || !((mask >> an) & 1u)) continue;
+            const float cf = an == 0 ? c0 : (an == 1 ? c1 : c2);
+            const float sc = cf * sigmoid_exact(vv[j]);
+            if (sc > a.thr) {
+                const size_t list = (size_t)b * C + (fld - 5);
+                const int pos = atomicAdd(cand_count + list, 1);
+                if (pos < a.cand_cap) {
+                    cand_score[list * a.cand_cap + pos] = sc;
+                    cand_index[list * a.cand_cap + pos] = box_base + an;
+                }
+            }
+        }
+    }
+}
+
+// yolo_head as a standalone op (reference code/yolo3/model.py:344-371): the public function of the
+// reference call surface; yolo_eval uses the fused decode kernels above instead.
+__global__ void __launch_bounds__(256)
+yolo_head_kernel(const float* __restrict__ feats, int ld, long long cells, int gh, int gw, int A, int C,
+                 const float* __restrict__ anchors, float in_h, float in_w, float* __restrict__ box_xy,
+                 float* __restrict__ box_wh, float* __restrict__ conf, float* __restrict__ cls, float* __restrict__ grid) {
+    const int E = C + 5;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= cells * A * E) return;
+    const int e = (int)(idx % E);
+    const long long ca = idx / E;  // cell * A + anchor
+    const int an = (int)(ca % A);
+    const long long cell = ca / A;
+    const int gx = (int)(cell % gw), gy = (int)((cell / gw) % gh);
+    const float v = __ldg(feats + cell * ld + (size_t)an * E + e);
+    if (e == 0) box_xy[ca * 2] = (sigmoid_exact(v) + (float)gx) / (float)gw;
+    else if (e == 1) box_xy[ca * 2 + 1] = (sigmoid_exact(v) + (float)gy) / (float)gh;
+    else if (e == 2) box_wh[ca * 2] = expf(v) * __ldg(anchors + an * 2) / in_w;
+    else if (e == 3) box_wh[ca * 2 + 1] = expf(v) * __ldg(anchors + an * 2 + 1) / in_h;
+    else if (e == 4) conf[ca] = sigmoid_exact(v);
+    else if (cls != nullptr) cls[ca * C + (e - 5)] = sigmoid_exact(v);
+    if (grid != nullptr && an == 0 && e < 2 && cell < (long long)gh * gw) grid[cell * 2 + e] = e == 0 ? (float)gx : (float)gy;
+}
+
 // ---- NMS ---------------------------------------------------------------------------
 __device__ __forceinline__ float iou_tf(const float4 bi, const float4 bj) {
     // NonMaxSuppressionV3 IOU (boxes are (y0,x0,y1,x1) with possibly swapped corners)
@@ -299,8 +402,18 @@ extern "C" int yr_decode_filter(const float* const feats[3], const float* image_
         }
         YR_CHECK_ARG(smem <= 200 * 1024, "decode: num_classes too large");
     }
-    dim3 grid(cdiv(a.total_boxes, DEC_BOXES), p->B);
-    decode_filter_kernel<<<grid, DEC_THREADS, smem, s>>>(a, image_shapes, boxes, cand_score, cand_index, cand_count);
+    bool aligned = ((uintptr_t)boxes % 16) == 0;
+    for (int k = 0; k < p->num_scales; ++k) aligned = aligned && ((uintptr_t)feats[k] % 16 == 0) && (p->ld[k] % 4 == 0);
+    if (p->score_threshold >= 0.01f && aligned) {
+        const int total_cells = a.total_boxes / 3;
+        dim3 grid(cdiv(total_cells, 8), p->B);
+        decode_sparse_kernel<<<grid, 256, 0, s>>>(a, image_shapes, boxes, cand_score, cand_index, cand_count, total_cells);
+    } else {
+        // dense variant (MAP mode runs with score_threshold = 0, reference code/main.py:175): CTA-level
+        // compaction keeps the atomics at one per (CTA, class)
+        dim3 grid(cdiv(a.total_boxes, DEC_BOXES), p->B);
+        decode_filter_kernel<<<grid, DEC_THREADS, smem, s>>>(a, image_shapes, boxes, cand_score, cand_index, cand_count);
+    }
     YR_CHECK_LAUNCH("decode_filter");
     return YR_OK;
 }
@@ -332,5 +445,20 @@ extern "C" int yr_pack_detections(const float* det, const int32_t* det_count, in
     pack_kernel<<<B, 128, (num_classes + 1) * sizeof(int), (cudaStream_t)stream>>>(
         det, det_count, num_classes, max_boxes, out_boxes_f, out_boxes_i, out_scores, out_classes, out_count);
     YR_CHECK_LAUNCH("pack");
+    return YR_OK;
+}
+
+extern "C" int yr_yolo_head(const float* feats, int ld, int B, int gh, int gw, int A, int C, const float* anchors_dev,
+                            int input_h, int input_w, float* box_xy, float* box_wh, float* box_confidence,
+                            float* box_class_probs, float* grid, void* stream) {
+    YR_CHECK_ARG(feats && anchors_dev && box_xy && box_wh && box_confidence, "yolo_head: null pointer");
+    YR_CHECK_ARG(B >= 1 && gh >= 1 && gw >= 1 && A >= 1 && C >= 1 && ld >= A * (C + 5), "yolo_head: bad sizes");
+    const long long cells = (long long)B * gh * gw;
+    const long long total = cells * A * (C + 5);
+    YR_CHECK_ARG(total < (1ll << 40), "yolo_head: too many elements");
+    yolo_head_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        feats, ld, cells, gh, gw, A, C, anchors_dev, (float)input_h, (float)input_w, box_xy, box_wh, box_confidence,
+        box_class_probs, grid);
+    YR_CHECK_LAUNCH("yolo_head");
     return YR_OK;
 }

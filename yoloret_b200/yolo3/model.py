@@ -117,6 +117,32 @@ def _as_cells(t: torch.Tensor, num_classes: int) -> Tuple[torch.Tensor, int]:
     return t, st[2]
 
 
+def yolo_head(feats: torch.Tensor, anchors, input_shape, calc_loss: bool = False):
+    """reference code/yolo3/model.py:344.  ``feats`` [B,gh,gw,A,5+C] float32 CUDA, ``anchors`` [A,2] (w,h px),
+    ``input_shape`` (h,w).  Returns ``(box_xy, box_wh, box_confidence, box_class_probs)`` or, with
+    ``calc_loss=True``, ``(grid, box_xy, box_wh, box_confidence)`` (grid [gh,gw,1,2])."""
+    anc = np.asarray(anchors, np.float32).reshape(-1, 2)
+    if not feats.is_cuda or feats.dtype != torch.float32 or feats.dim() != 5 or feats.shape[3] != len(anc):
+        raise ValueError("yolo_head expects a float32 CUDA tensor [B,gh,gw,%d,5+C]" % len(anc))
+    B, gh, gw, A, E = (int(v) for v in feats.shape)
+    f, ld = _as_cells_generic(feats, A, E)
+    dev = feats.device
+    anc_d = torch.from_numpy(anc).to(dev)
+    xy = torch.empty(B, gh, gw, A, 2, dtype=torch.float32, device=dev)
+    wh = torch.empty_like(xy)
+    conf = torch.empty(B, gh, gw, A, 1, dtype=torch.float32, device=dev)
+    cls = None if calc_loss else torch.empty(B, gh, gw, A, E - 5, dtype=torch.float32, device=dev)
+    grid = torch.empty(gh, gw, 1, 2, dtype=torch.float32, device=dev) if calc_loss else None
+    _lib.check(_lib.lib().yr_yolo_head(f.data_ptr(), ld, B, gh, gw, A, E - 5, anc_d.data_ptr(), int(input_shape[0]),
+                                       int(input_shape[1]), xy.data_ptr(), wh.data_ptr(), conf.data_ptr(),
+                                       cls.data_ptr() if cls is not None else None,
+                                       grid.data_ptr() if grid is not None else None,
+                                       torch.cuda.current_stream(dev).cuda_stream), "yr_yolo_head")
+    if calc_loss:
+        return grid, xy, wh, conf
+    return xy, wh, conf, cls
+
+
 def yolo_eval(yolo_outputs, anchors, num_scales, num_classes, image_shape, max_boxes=20, score_threshold=.6,
               iou_threshold=.5, zoom_outputs=None):
     """reference code/yolo3/model.py:431.  Returns (boxes_ int32 [N,4] (ymin,xmin,ymax,xmax),
