@@ -46,7 +46,8 @@ typedef enum yr_op_kind {
     YR_OP_DW = 2,        /* depthwise kxk conv, k in {3,5}, stride in {1,2} (+folded BN +act) */
     YR_OP_RESAMPLE = 3,  /* nearest x2 up-sampling / 2x2 / 4x4 max-pooling into a channel slice */
     YR_OP_RFCR = 4,      /* fused RFCR fusion: 4x 1x1 conv + resize + weighted sum */
-    YR_OP_SE = 5         /* squeeze-excite gate: global mean -> FC -> swish -> FC -> sigmoid */
+    YR_OP_SE = 5,        /* squeeze-excite gate: global mean -> FC -> swish -> FC -> sigmoid */
+    YR_OP_SE_FC = 6      /* the same gate from the channel sums a DW op left in `aux` (fused squeeze) */
 } yr_op_kind;
 
 typedef enum yr_resample_mode { YR_UP2 = 0, YR_POOL2 = 1, YR_POOL4 = 2 } yr_resample_mode;
@@ -81,6 +82,11 @@ typedef enum yr_resample_mode { YR_UP2 = 0, YR_POOL2 = 1, YR_POOL4 = 2 } yr_resa
  *           out[b,h,w,:] = a0*W1.b1[h/2,w/2] + a1*W2.b2[h,w]
  *                        + a2*max_{2x2}(W3.b3) + a3*W4.max_{4x4}(b4)
  *           (H,W = output grid).  rfcr_module + WeightedSum, model.py:117-157,190.
+ *           aux optional [B][yr_dw_se_slots(op)][C]: per-CTA sums of the op's OUTPUT over its pixels
+ *               (the squeeze of a following SEBlock, fused; deterministic, no atomics).
+ *  SE_FC    in = the aux buffer of the producing DW op [B][K2 slots][C=F]; H,W = spatial size of the
+ *           squeezed tensor; w = [w1^T R x F | w2 R x F] (first FC TRANSPOSED), bias = b1[R] then b2[F];
+ *           N = R; out = gate [B][F].
  *  SE       in [B,H,W,ld_in] C=F channels; w = [F][R] then [R][F] (w2 = w + F*R),
  *           bias = b1[R] then b2[F]; N = R; out = gate [B][F].
  *           SEBlock, efficientnet.py:406-438.
@@ -107,12 +113,14 @@ typedef struct yr_op {
     const float* res;
     const float* scale;
     const float* w_tc;       /* PW: weight image made by yr_pw_tc_pack (tensor-core variant), or NULL */
+    float* aux;              /* DW: squeeze-excite partial sums (see above), or NULL */
 } yr_op;
 
 /* Library identity / errors. */
 int yr_version(void);
 const char* yr_last_error(void);
 int yr_sizeof_op(void); /* sizeof(yr_op), for binding self-checks */
+int yr_dw_se_slots(const yr_op* op); /* slots per image of a DW op's aux buffer (negative = invalid op) */
 
 /* Executes ops[0..n_ops) in order on `stream`.  The network forward
  * (reference yolov3_body, code/yolo3/model.py:170-342, called from

@@ -207,6 +207,51 @@ def test_se_parity(built_lib, HW, F_, R):
     torch.testing.assert_close(out.cpu().double(), ref, rtol=RTOL, atol=ATOL)
 
 
+@pytest.mark.parametrize("B,H,W,F_,R,k,s", [(3, 13, 13, 512, 128, 3, 1), (2, 26, 26, 256, 64, 3, 1), (2, 20, 12, 128, 32, 3, 1),
+                                             (2, 9, 7, 40, 10, 5, 2), (1, 8, 8, 1392, 58, 5, 1)])
+def test_fused_squeeze_excite(built_lib, B, H, W, F_, R, k, s):
+    """Depthwise op with the fused squeeze (aux partial sums) + SE_FC == mean/FC/swish/FC/sigmoid of its output;
+    bit-identical run to run (no atomics)."""
+    import ctypes as C
+    x = _rand(B, H, W, F_, seed=1)
+    w = _rand(k * k, F_, seed=2, scale=0.3)
+    bias = _rand(F_, seed=3)
+    dwref, (Ho, Wo, pt, pl) = _dw_ref(x, w, bias, k, s, "swish")
+    w1, b1 = _rand(F_, R, seed=4, scale=F_ ** -0.5), _rand(R, seed=5, scale=0.1)
+    w2, b2 = _rand(R, F_, seed=6, scale=R ** -0.5), _rand(F_, seed=7, scale=0.1)
+    m = dwref.mean(dim=(1, 2))
+    h = m @ w1.double() + b1.double()
+    h = h * torch.sigmoid(h)
+    ref = torch.sigmoid(h @ w2.double() + b2.double())
+    xd, wd, bd = x.cuda(), w.cuda(), bias.cuda()
+    out = torch.full((B, Ho, Wo, F_), float("nan"), device="cuda")
+    op = YrOp()
+    op.kind, op.act = _lib.OP_DW, ACT["swish"]
+    op.B, op.H, op.W, op.C, op.Ho, op.Wo, op.N = B, H, W, F_, Ho, Wo, F_
+    op.k, op.stride, op.pad_t, op.pad_l, op.ld_in, op.ld_out = k, s, pt, pl, F_, F_
+    op.in_, op.out, op.w, op.bias = xd.data_ptr(), out.data_ptr(), wd.data_ptr(), bd.data_ptr()
+    slots = built_lib.yr_dw_se_slots(C.byref(op))
+    assert slots > 0
+    gates = []
+    for _ in range(2):
+        part = torch.full((B, slots, F_), float("nan"), device="cuda")
+        op.aux = part.data_ptr()
+        run_op(op)
+        torch.testing.assert_close(out.cpu().double(), dwref, rtol=RTOL, atol=ATOL)
+        torch.testing.assert_close(part.sum(1).cpu().double() / (Ho * Wo), m, rtol=1e-5, atol=1e-5)
+        wcat = torch.cat([w1.t().reshape(-1), w2.reshape(-1)]).cuda()
+        bcat = torch.cat([b1, b2]).cuda()
+        gate = torch.full((B, F_), float("nan"), device="cuda")
+        fc = YrOp()
+        fc.kind = _lib.OP_SE_FC
+        fc.B, fc.H, fc.W, fc.C, fc.N, fc.K2 = B, Ho, Wo, F_, R, slots
+        fc.in_, fc.out, fc.w, fc.bias = part.data_ptr(), gate.data_ptr(), wcat.data_ptr(), bcat.data_ptr()
+        run_op(fc)
+        torch.testing.assert_close(gate.cpu().double(), ref, rtol=RTOL, atol=ATOL)
+        gates.append(gate.clone())
+    assert torch.equal(gates[0], gates[1])
+
+
 def test_bad_arguments_fail_loudly(built_lib):
     op = YrOp()
     op.kind = _lib.OP_PW

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libyoloret_b200.so")
 
 # enums (include/yoloret_b200.h)
 ACT_NONE, ACT_RELU6, ACT_SWISH = 0, 1, 2
-OP_STEM, OP_PW, OP_DW, OP_RESAMPLE, OP_RFCR, OP_SE = 0, 1, 2, 3, 4, 5
+OP_STEM, OP_PW, OP_DW, OP_RESAMPLE, OP_RFCR, OP_SE, OP_SE_FC = 0, 1, 2, 3, 4, 5, 6
 UP2, POOL2, POOL4 = 0, 1, 2
 PW_AUTO, PW_SIMT, PW_TC = 0, 1, 2
 
@@ -32,7 +32,7 @@ class YrOp(C.Structure):
         ("in_", C.c_void_p), ("in2", C.c_void_p), ("in3", C.c_void_p), ("in4", C.c_void_p),
         ("out", C.c_void_p),
         ("w", C.c_void_p), ("bias", C.c_void_p), ("res", C.c_void_p), ("scale", C.c_void_p),
-        ("w_tc", C.c_void_p),
+        ("w_tc", C.c_void_p), ("aux", C.c_void_p),
     ]
 
 
@@ -62,6 +62,7 @@ SYMBOLS = {
     "yr_version": (C.c_int, []),
     "yr_last_error": (C.c_char_p, []),
     "yr_sizeof_op": (C.c_int, []),
+    "yr_dw_se_slots": (C.c_int, [C.POINTER(YrOp)]),
     "yr_run_ops": (C.c_int, [C.POINTER(YrOp), C.c_int, _P]),
     "yr_pw_tc_packed_floats": (C.c_int64, [C.c_int, C.c_int]),
     "yr_pw_tc_pack": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),

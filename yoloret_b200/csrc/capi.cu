@@ -59,6 +59,15 @@ extern "C" int yr_version(void) { return 100; }
 extern "C" const char* yr_last_error(void) { return g_err; }
 extern "C" int yr_sizeof_op(void) { return (int)sizeof(yr_op); }
 
+extern "C" int yr_dw_se_slots(const yr_op* op) {
+    if (!op || op->kind != YR_OP_DW || op->C <= 0 || op->C % 4 || (op->k != 3 && op->k != 5) ||
+        (op->stride != 1 && op->stride != 2) || op->Ho <= 0 || op->Wo <= 0) {
+        set_error("dw_se_slots: not a valid depthwise op");
+        return YR_ERR_INVALID;
+    }
+    return dw_se_slots(*op);
+}
+
 extern "C" int yr_run_ops(const yr_op* ops, int n_ops, void* stream) {
     YR_CHECK_ARG(ops != nullptr || n_ops == 0, "run_ops: null ops");
     cudaStream_t s = (cudaStream_t)stream;
@@ -74,6 +83,7 @@ extern "C" int yr_run_ops(const yr_op* ops, int n_ops, void* stream) {
             case YR_OP_RESAMPLE: rc = launch_resample(op, s); break;
             case YR_OP_RFCR: rc = launch_rfcr(op, s); break;
             case YR_OP_SE: rc = launch_se(op, s); break;
+            case YR_OP_SE_FC: rc = launch_se_fc(op, s); break;
             default:
                 set_error("run_ops: op %d has unknown kind %d", i, op.kind);
                 return YR_ERR_INVALID;

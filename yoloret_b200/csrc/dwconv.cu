@@ -16,14 +16,18 @@ namespace yr {
 template <int KS, int S, int TH, int TW, int ACT>
 __global__ void __launch_bounds__(128)
 dw_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ wgt, const float* __restrict__ bias,
-          float* __restrict__ out, int ld_out, int H, int W, int C, int Ho, int Wo, int pad_t, int pad_l) {
+          float* __restrict__ out, int ld_out, int H, int W, int C, int Ho, int Wo, int pad_t, int pad_l,
+          float* __restrict__ part) {
     constexpr int IN_ROWS = (TH - 1) * S + KS;
     constexpr int IN_COLS = (TW - 1) * S + KS;
+    extern __shared__ __align__(16) float s_sum[];  // [C], only when part != nullptr
     const int C4 = C >> 2;
     const int wtiles = (Wo + TW - 1) / TW;
     const int item = blockIdx.x * 128 + threadIdx.x;
-    if (item >= wtiles * C4) return;
-    const int c = (item % C4) * 4;
+    const bool active = item < wtiles * C4;
+    float4 ps = make_float4(0.f, 0.f, 0.f, 0.f);  // sum of this thread's outputs (squeeze-excite mean)
+    const int c = active ? (item % C4) * 4 : 0;
+    if (active) {
     const int wo0 = (item / C4) * TW;
     const int ho0 = blockIdx.y * TH;
     const int b = blockIdx.z;
@@ -87,7 +91,28 @@ dw_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ wgt
             v.z = apply_act<ACT>(acc[t][o].z + bv.z);
             v.w = apply_act<ACT>(acc[t][o].w + bv.w);
             st4(out + (((size_t)b * Ho + ho) * Wo + wo) * ld_out + c, v);
+            ps.x += v.x; ps.y += v.y; ps.z += v.z; ps.w += v.w;
         }
+    }
+    }  // active
+    if (part != nullptr) {
+        // Squeeze-excite 'Mean' (reference code/yolo3/efficientnet.py:391-403,419) fused here: a
+        // deterministic per-CTA channel sum (threads that share a channel group add in rank order),
+        // one [C] slot per CTA; se_fc_kernel adds the slots in index order.  No atomics: the result
+        // is bit-identical run to run, which the bit-exact NMS tests downstream rely on.
+        for (int i = threadIdx.x; i < C; i += 128) s_sum[i] = 0.0f;
+        __syncthreads();
+        const int G = (128 + C4 - 1) / C4;
+        for (int g = 0; g < G; ++g) {
+            if (active && (int)threadIdx.x / C4 == g) {
+                float4 a = *reinterpret_cast<float4*>(s_sum + c);
+                a.x += ps.x; a.y += ps.y; a.z += ps.z; a.w += ps.w;
+                *reinterpret_cast<float4*>(s_sum + c) = a;
+            }
+            __syncthreads();
+        }
+        float* dst = part + (((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * C;
+        for (int i = threadIdx.x; i < C4; i += 128) st4(dst + i * 4, *reinterpret_cast<float4*>(s_sum + i * 4));
     }
 }
 
@@ -95,10 +120,24 @@ template <int KS, int S, int TH, int TW, int ACT>
 static int launch_dw_cfg(const yr_op& op, cudaStream_t s) {
     const int items = cdiv(op.Wo, TW) * (op.C / 4);
     dim3 grid(cdiv(items, 128), cdiv(op.Ho, TH), op.B);
-    dw_kernel<KS, S, TH, TW, ACT><<<grid, 128, 0, s>>>((const float*)op.in, op.ld_in, op.w, op.bias, (float*)op.out,
-                                                        op.ld_out, op.H, op.W, op.C, op.Ho, op.Wo, op.pad_t, op.pad_l);
+    const size_t smem = op.aux ? (size_t)op.C * sizeof(float) : 0;
+    dw_kernel<KS, S, TH, TW, ACT><<<grid, 128, smem, s>>>((const float*)op.in, op.ld_in, op.w, op.bias, (float*)op.out,
+                                                           op.ld_out, op.H, op.W, op.C, op.Ho, op.Wo, op.pad_t, op.pad_l,
+                                                           op.aux);
     YR_CHECK_LAUNCH("dw");
     return YR_OK;
+}
+
+static void dw_tile(int k, int stride, int& th, int& tw) {
+    th = (k == 3) ? 2 : 1;
+    tw = (k == 5 && stride == 2) ? 2 : 4;
+}
+
+// Number of [C] partial-sum slots per image the fused squeeze-excite sum of this DW op writes.
+int dw_se_slots(const yr_op& op) {
+    int th, tw;
+    dw_tile(op.k, op.stride, th, tw);
+    return cdiv(cdiv(op.Wo, tw) * (op.C / 4), 128) * cdiv(op.Ho, th);
 }
 
 template <int ACT>
@@ -118,6 +157,7 @@ int launch_dw(const yr_op& op, cudaStream_t s) {
     YR_CHECK_ARG(((uintptr_t)op.in | (uintptr_t)op.out | (uintptr_t)op.w | (uintptr_t)op.bias) % 16 == 0,
                  "dw: pointers must be 16-byte aligned");
     YR_CHECK_ARG(op.B <= 65535 && cdiv(op.Ho, 1) <= 65535, "dw: grid too large");
+    YR_CHECK_ARG(!op.aux || ((uintptr_t)op.aux % 16 == 0 && op.C <= 12288), "dw: bad squeeze-excite partial buffer");
     switch (op.act) {
         case YR_ACT_NONE: return launch_dw_act<YR_ACT_NONE>(op, s);
         case YR_ACT_RELU6: return launch_dw_act<YR_ACT_RELU6>(op, s);

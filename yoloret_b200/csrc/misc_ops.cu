@@ -403,4 +403,60 @@ int launch_se(const yr_op& op, cudaStream_t s) {
     return YR_OK;
 }
 
+// ---------------------------------------------------------------------------------
+// Squeeze-excite gate from the per-CTA channel sums the depthwise kernel left behind
+// (dwconv.cu): the global mean never re-reads the activation.  One CTA per image.
+//   w = [w1t R x F | w2 R x F],  bias = [b1 R | b2 F]   (w1 TRANSPOSED so a warp reads it coalesced)
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+se_fc_kernel(const float* __restrict__ part, int slots, int HW, int F, int R, const float* __restrict__ w1t,
+             const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+             float* __restrict__ gate) {
+    extern __shared__ __align__(16) float sm[];
+    float* mean = sm;      // [F]
+    float* hid = sm + F;   // [R]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* pb = part + (size_t)blockIdx.x * slots * F;
+    for (int f4 = tid; f4 < (F >> 2); f4 += 256) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int sl = 0; sl < slots; ++sl) {  // fixed order: deterministic
+            const float4 v = ldg4(pb + (size_t)sl * F + f4 * 4);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        const float d = (float)HW;
+        st4(mean + f4 * 4, make_float4(a.x / d, a.y / d, a.z / d, a.w / d));
+    }
+    __syncthreads();
+    for (int r = warp; r < R; r += 8) {
+        float a = 0.f;
+        for (int f = lane; f < F; f += 32) a = fmaf(mean[f], __ldg(w1t + (size_t)r * F + f), a);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) {
+            a += __ldg(b1 + r);
+            hid[r] = a * (1.0f / (1.0f + expf(-a)));
+        }
+    }
+    __syncthreads();
+    for (int f = tid; f < F; f += 256) {
+        float a = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < R; ++r) a = fmaf(hid[r], __ldg(w2 + (size_t)r * F + f), a);
+        a += __ldg(b2 + f);
+        gate[(size_t)blockIdx.x * F + f] = 1.0f / (1.0f + expf(-a));
+    }
+}
+
+int launch_se_fc(const yr_op& op, cudaStream_t s) {
+    YR_CHECK_ARG(op.in && op.out && op.w && op.bias, "se_fc: null pointer");
+    const int F = op.C, R = op.N, slots = op.K2;
+    YR_CHECK_ARG(F % 4 == 0 && R > 0 && slots > 0 && op.H > 0 && op.W > 0, "se_fc: unsupported F=%d R=%d slots=%d", F, R, slots);
+    const size_t smem = (size_t)(F + R) * sizeof(float);
+    YR_CHECK_ARG(smem <= 48 * 1024, "se_fc: F too large");
+    se_fc_kernel<<<op.B, 256, smem, s>>>((const float*)op.in, slots, op.H * op.W, F, R, op.w, op.bias,
+                                         op.w + (size_t)F * R, op.bias + R, (float*)op.out);
+    YR_CHECK_LAUNCH("se_fc");
+    return YR_OK;
+}
+
 }  // namespace yr

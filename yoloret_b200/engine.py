@@ -60,7 +60,8 @@ class Engine:
     def __init__(self, model_name: str, num_classes: int, input_hw: Tuple[int, int], batch: int,
                  weights: Dict[str, np.ndarray], anchors: np.ndarray, micro_batch: Optional[int] = None,
                  num_scales: int = 3, max_boxes: int = 20, cand_cap: Optional[int] = None,
-                 device: Optional[torch.device] = None, pw_variant: int = _lib.PW_AUTO, input_u8: bool = False):
+                 device: Optional[torch.device] = None, pw_variant: int = _lib.PW_AUTO, input_u8: bool = False,
+                 fuse_se: bool = True):
         if not torch.cuda.is_available():
             raise _lib.YrError("yoloret_b200.Engine needs a CUDA device (no CPU fallback exists)")
         self.lib = _lib.lib()
@@ -73,6 +74,7 @@ class Engine:
         self.anchors = np.asarray(anchors, dtype=np.float32).reshape(-1, 2)
         self.input_u8 = input_u8
         self.pw_variant = pw_variant
+        self.fuse_se = fuse_se
         self.cand_cap_arg = cand_cap
         self._check_weights(weights)
         self._alloc()
@@ -121,6 +123,8 @@ class Engine:
         """Folds BN, pads channels to the device layout and uploads."""
         self.wdev: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
         self.wtc: Dict[int, torch.Tensor] = {}   # tensor-core weight images of the pointwise layers
+        self.se_fused: Dict[int, bool] = {}      # SE layers whose squeeze rides in the depthwise epilogue
+        self.se_part: Dict[int, torch.Tensor] = {}
         for i, L in enumerate(self.net.layers):
             if L.kind == "pw":
                 k = w[L.conv + "/kernel"][0, 0].astype(np.float64)          # [Cin, Cout]
@@ -144,6 +148,12 @@ class Engine:
                 w1 = _expand_rows(w[c1 + "/kernel"][0, 0].astype(np.float64), L.inp[0].segs)      # [Fp, R]
                 w2 = _pad_cols(w[c2 + "/kernel"][0, 0].astype(np.float64), L.inp[0].C)            # [R, Fp]
                 b2 = _pad_cols(w[c2 + "/bias"].astype(np.float64), L.inp[0].C)
+                prev = self.net.layers[i - 1] if i > 0 else None
+                fused = (self.fuse_se and prev is not None and prev.kind == "dw" and prev.out.buf is L.inp[0].buf
+                         and prev.out.off == L.inp[0].off)
+                if fused:  # squeeze fused into the producing depthwise op; first FC stored transposed
+                    self.se_fused[i] = True
+                    w1 = np.ascontiguousarray(w1.T)                                               # [R, Fp]
                 wcat = np.concatenate([w1.ravel(), w2.ravel()])
                 bcat = np.concatenate([w[c1 + "/bias"].astype(np.float64), b2])
                 self.wdev[i] = (self._dev(wcat), self._dev(bcat))
@@ -211,6 +221,13 @@ class Engine:
                     o.scale = gate_ptr[id(L.gate)]
             elif L.kind == "dw":
                 o.kind = _lib.OP_DW
+                if self.se_fused.get(i + 1):
+                    if i + 1 not in self.se_part:
+                        slots = int(self.lib.yr_dw_se_slots(C.byref(o)))
+                        if slots <= 0:
+                            _lib.check(slots, "yr_dw_se_slots")
+                        self.se_part[i + 1] = torch.zeros(self.micro, slots, o.C, dtype=torch.float32, device=self.device)
+                    o.aux = self.se_part[i + 1].data_ptr()
             elif L.kind == "resample":
                 o.kind = _lib.OP_RESAMPLE
                 o.mode = _MODE[L.mode]
@@ -218,6 +235,10 @@ class Engine:
                 o.kind = _lib.OP_SE
                 o.N = L.extra["reduced"]
                 gate_ptr[id(L)] = o.out
+                if self.se_fused.get(i):
+                    o.kind = _lib.OP_SE_FC
+                    o.in_ = self.se_part[i].data_ptr()
+                    o.K2 = int(self.se_part[i].shape[1])
             elif L.kind == "rfcr":
                 o.kind = _lib.OP_RFCR
                 b1, b2, b3, b4 = L.inp
