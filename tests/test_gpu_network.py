@@ -156,6 +156,30 @@ def test_detect_batch_graph_equals_eager(built_lib, anchors, tmp_path):
     assert total > 0
 
 
+def test_detect_stream_equals_detect_batch(built_lib, anchors, tmp_path):
+    """The pipelined API returns, batch by batch and in order, exactly what the blocking call returns."""
+    hw, ncls, B = (96, 96), 20, 3
+    nd = NetDef("mobilenetv2x75", ncls, hw)
+    w = synthetic_weights(nd.weight_shapes, ncls, seed=8)
+    (tmp_path / "a.txt").write_text(",".join("%g,%g" % (a * 96 / 416, b * 96 / 416) for a, b in anchors))
+    (tmp_path / "c.txt").write_text("\n".join("c%d" % i for i in range(ncls)) + "\n")
+    yolo = YOLO({"backbone": "mobilenetv2x75", "classes_path": str(tmp_path / "c.txt"),
+                 "anchors_path": str(tmp_path / "a.txt"), "input_size": hw, "score": 0.05, "nms": 0.5, "weights": w,
+                 "batch": B, "quiet": True})
+    g = torch.Generator().manual_seed(3)
+    batches = [torch.rand(B, hw[0], hw[1], 3, generator=g).pin_memory() for _ in range(5)]
+    ref = [yolo.detect_batch(x) for x in batches]
+    got = list(yolo.detect_stream(iter(batches)))
+    assert len(got) == len(ref) == 5
+    for r, q in zip(ref, got):
+        for a, c in zip(r, q):
+            assert all(np.array_equal(u, v) for u, v in zip(a, c))
+    assert sum(len(a[1]) for r in ref for a in r) > 0
+    assert list(yolo.detect_stream(iter([]))) == []
+    with pytest.raises(ValueError):
+        list(yolo.detect_stream(iter([torch.zeros(1, 96, 96, 3)])))
+
+
 def test_api_errors(built_lib):
     with pytest.raises(ValueError):
         yolov3_body((1, 100, 100, 3), "mobilenetv2x75", 3, num_classes=20)  # not a multiple of 32

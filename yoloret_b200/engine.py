@@ -110,7 +110,9 @@ class Engine:
                 self.buf_t[b.name] = self.arena[offs[b.name]:offs[b.name] + n].view(self.micro, b.H, b.W, b.ld)
         self.arena_bytes = total * 4
         in_dtype = torch.uint8 if self.input_u8 else torch.float32
-        self.input = torch.zeros(self.batch, self.input_hw[0], self.input_hw[1], 3, dtype=in_dtype, device=dev)
+        # two input slots: slot 1 exists so a streaming caller can upload batch i+1 while batch i computes
+        self.inputs = [torch.zeros(self.batch, self.input_hw[0], self.input_hw[1], 3, dtype=in_dtype, device=dev)]
+        self.input = self.inputs[0]
         grids = [(v.H, v.W) for v in net.outputs]
         self.pp = PostProcess(self.batch, grids, self.num_classes, self.anchors, self.num_scales, self.max_boxes,
                               device=dev, cand_cap=self.cand_cap_arg)
@@ -178,17 +180,22 @@ class Engine:
         return packed
 
     # ---- plan ---------------------------------------------------------------------
-    def _ptr(self, v: View, chunk0: int) -> int:
+    def input_slot(self, slot: int) -> torch.Tensor:
+        while len(self.inputs) <= slot:
+            self.inputs.append(torch.zeros_like(self.inputs[0]))
+        return self.inputs[slot]
+
+    def _ptr(self, v: View, chunk0: int, slot: int = 0) -> int:
         """Device address of a view for the micro-batch starting at image ``chunk0``."""
-        t = self.input if v.buf.name == "input" else self.buf_t[v.buf.name]
+        t = self.input_slot(slot) if v.buf.name == "input" else self.buf_t[v.buf.name]
         base = t.data_ptr() + v.off * t.element_size()
         if v.buf.full_batch:
             base += chunk0 * v.buf.H * v.buf.W * v.buf.ld * t.element_size()
         return base
 
-    def build_plan(self, chunk0: int, nb: int):
-        """yr_op array for images [chunk0, chunk0+nb)."""
-        key = (chunk0, nb)
+    def build_plan(self, chunk0: int, nb: int, slot: int = 0):
+        """yr_op array for images [chunk0, chunk0+nb) reading input slot ``slot``."""
+        key = (chunk0, nb, slot)
         if key in self._plans:
             return self._plans[key]
         ops = (YrOp * len(self.net.layers))()
@@ -202,7 +209,7 @@ class Engine:
             o.k, o.stride = L.k, L.stride
             o.pad_t, o.pad_l = L.extra.get("pad_t", 0), L.extra.get("pad_l", 0)
             o.ld_in, o.ld_out = x.buf.ld, L.out.buf.ld
-            o.in_ = self._ptr(x, chunk0)
+            o.in_ = self._ptr(x, chunk0, slot)
             o.out = self._ptr(L.out, chunk0)
             if i in self.wdev:
                 o.w, o.bias = self.wdev[i][0].data_ptr(), self.wdev[i][1].data_ptr()
@@ -254,13 +261,13 @@ class Engine:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def run_network(self):
-        """yolov3_body forward over self.input -> y buffers, micro-batch by micro-batch."""
+    def run_network(self, slot: int = 0):
+        """yolov3_body forward over input slot ``slot`` -> y buffers, micro-batch by micro-batch."""
         st = self._stream()
         n = 0
         for c0 in range(0, self.batch, self.micro):
             nb = min(self.micro, self.batch - c0)
-            ops, cnt = self.build_plan(c0, nb)
+            ops, cnt = self.build_plan(c0, nb, slot)
             _lib.check(self.lib.yr_run_ops(ops, cnt, st), "yr_run_ops")
             n += cnt
         return n
@@ -281,20 +288,20 @@ class Engine:
         ld = [v.buf.ld for v in self.net.outputs[:self.num_scales]]
         return self.pp.run(ptrs, ld, score_threshold, iou_threshold, self._stream())
 
-    def step(self, score_threshold: float, iou_threshold: float) -> int:
-        """One full pass: network + post-process on whatever is in self.input. Returns #kernel launches."""
-        n = self.run_network()
+    def step(self, score_threshold: float, iou_threshold: float, slot: int = 0) -> int:
+        """One full pass: network + post-process on whatever is in the input slot. Returns #kernel launches."""
+        n = self.run_network(slot)
         self.run_postprocess(score_threshold, iou_threshold)
         self.launches_per_forward = n + 3
         return n + 3
 
-    def capture(self, score_threshold: float, iou_threshold: float):
+    def capture(self, score_threshold: float, iou_threshold: float, slot: int = 0):
         """Captures step() into a CUDA graph (launch-bound at small batch: ~90 kernels / micro-batch)."""
-        self.step(score_threshold, iou_threshold)  # warm-up: sets func attributes outside capture
+        self.step(score_threshold, iou_threshold, slot)  # warm-up: sets func attributes outside capture
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self.step(score_threshold, iou_threshold)
+            self.step(score_threshold, iou_threshold, slot)
         self._graph = g
         return g
 

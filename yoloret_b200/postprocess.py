@@ -61,6 +61,7 @@ class PostProcess:
         self.wire = self.flat[:self.wire_words]
         self._hdr, self._slots = hdr, slots
         self.host_flat = torch.zeros(self.flat.numel(), dtype=i32).pin_memory()
+        self.host_flat2 = None  # second pinned landing buffer, allocated by streaming callers
         self.image_shapes = torch.zeros(B, 2, dtype=f32, device=dev)
         self._shapes_host = None
         self.workspace_bytes = sum(t.numel() * t.element_size() for t in (
@@ -125,6 +126,15 @@ class PostProcess:
 
     def d2h_bytes(self, with_float_boxes: bool = False) -> int:
         return (self.flat.numel() if with_float_boxes else self.wire_words) * 4
+
+    def enqueue_read(self, slot: int = 0) -> torch.Tensor:
+        """Asynchronous device->host copy of the wire words on the current stream into pinned landing
+        buffer ``slot`` (0/1); the caller synchronises (event) before touching the returned tensor."""
+        if slot == 1 and self.host_flat2 is None:
+            self.host_flat2 = torch.zeros(self.wire_words, dtype=torch.int32).pin_memory()
+        dst = (self.host_flat if slot == 0 else self.host_flat2)[:self.wire_words]
+        dst.copy_(self.wire, non_blocking=True)
+        return dst
 
     def read_wire(self, with_float_boxes: bool = False) -> np.ndarray:
         """ONE device->host copy of the wire buffer into pinned host memory (synchronises the stream)."""

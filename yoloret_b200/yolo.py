@@ -177,3 +177,70 @@ class YOLO(object):
         if unpack:
             return e.results()
         return e.pp.padded_views(e.pp.read_wire())
+
+    def detect_stream(self, batches, image_shapes=None, unpack: bool = True):
+        """Pipelined ``detect_batch`` over an iterable of host batches (pinned memory recommended): yields one
+        result per batch, in order.  The host->device upload of batch i+1 runs on a copy stream into a
+        second input slot while batch i computes, and each batch's detections come back with ONE
+        device->host copy, so in steady state a step costs max(compute, PCIe) instead of their sum.
+        Every batch is still uploaded, computed and read back; nothing is cached between batches."""
+        e = self.engine
+        dev = e.device
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._graphs = {}
+        e.pp.set_image_shapes(image_shapes if image_shapes is not None else self.input_shape)
+        for slot in (0, 1):
+            if slot not in self._graphs:
+                e.input_slot(slot)
+                self._graphs[slot] = e.capture(self.score, self.nms, slot)
+        cs = self._copy_stream
+        uploaded = [torch.cuda.Event(), torch.cuda.Event()]   # input slot filled
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]   # input slot free again (its graph finished)
+        landed = [torch.cuda.Event(), torch.cuda.Event()]     # wire copy of that step on the host
+
+        def upload(images, slot, first_use):
+            if tuple(images.shape) != tuple(e.input.shape) or images.dtype != e.input.dtype:
+                raise ValueError("expected %s %s, got %s %s" % (tuple(e.input.shape), e.input.dtype,
+                                                                tuple(images.shape), images.dtype))
+            with torch.cuda.stream(cs):
+                if not first_use:
+                    cs.wait_event(consumed[slot])
+                e.input_slot(slot).copy_(images, non_blocking=True)
+                uploaded[slot].record(cs)
+
+        it = iter(batches)
+        try:
+            cur = next(it)
+        except StopIteration:
+            return
+        cs.wait_stream(main)
+        upload(cur, 0, True)
+        i = 0
+        pending = None  # (slot, host wire tensor) of the previous step, not yet yielded
+        while cur is not None:
+            slot = i & 1
+            main.wait_event(uploaded[slot])
+            self._graphs[slot].replay()
+            consumed[slot].record(main)
+            host = e.pp.enqueue_read(slot)
+            landed[slot].record(main)
+            try:
+                nxt = next(it)
+            except StopIteration:
+                nxt = None
+            if nxt is not None:
+                upload(nxt, (i + 1) & 1, i == 0)
+            if pending is not None:
+                ps, ph = pending
+                landed[ps].synchronize()
+                w = ph.numpy()
+                yield e.pp.unpack_wire(w) if unpack else e.pp.padded_views(w)
+            pending = (slot, host)
+            cur = nxt
+            i += 1
+        ps, ph = pending
+        landed[ps].synchronize()
+        w = ph.numpy()
+        yield e.pp.unpack_wire(w) if unpack else e.pp.padded_views(w)
