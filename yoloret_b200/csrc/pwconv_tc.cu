@@ -23,6 +23,7 @@
 //   warps 6-9   epilogue   tcgen05.ld TMEM -> registers -> 32x33 smem transpose -> bias, activation,
 //                          residual -> fully coalesced 128-byte row stores (masking the N/M tails).
 #include "yr_common.cuh"
+#include <stdlib.h>
 #include <cuda.h>  // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved at run time
 
 namespace yr {
@@ -31,11 +32,14 @@ namespace tc {
 constexpr int BM = 128;                      // rows per tile = UMMA M
 constexpr int BK = 32;                       // fp32 per k-block = one 128-byte swizzle row
 constexpr int A_TILE_BYTES = BM * BK * 4;    // 16 KB (raw/hi) ; lo tile has the same size
-constexpr int NUM_THREADS = 320;
+constexpr int NUM_CONVERTERS = 256;          // converter threads: 2 groups of 4 warps, alternating k-blocks
+constexpr int NUM_EPILOGUE = 256;            // epilogue threads: 2 groups of 4 warps, alternating tiles
+constexpr int NUM_THREADS = 64 + NUM_CONVERTERS + NUM_EPILOGUE;  // + producer warp + MMA warp
 constexpr int EPI_LD = 36;                   // padded row (floats) of the per-warp transpose buffer
-constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
+constexpr int EPI_GROUP_BYTES = 4 * 32 * EPI_LD * 4 + 1024;  // per epilogue group: 4 transpose buffers + the n tile's bias
 constexpr int SMEM_LIMIT = 232448;           // 227 KB per CTA
-constexpr int MAX_A_STAGES = 8, MAX_B_SLOTS = 24;
+constexpr int MAX_A_STAGES = 12, MAX_L_SLOTS = 4, MAX_B_SLOTS = 24, MAX_ACC = 8;
+constexpr int BAR_BYTES = 1024;
 
 struct Params {
     const float* wp;      // packed weight image, see pack_kernel
@@ -45,8 +49,9 @@ struct Params {
     float* out;
     int M, K, N, BN, n_tiles, m_tiles, KB;
     int ld_out, ld_res, rows_per_img, act;
-    int nA, nB, resident, tmem_cols, acc_stride, items_per_cta, total_items;
+    int nA, nL, nB, nAcc, nEpi, resident, tmem_cols, acc_stride, items_per_cta, total_items;
     uint32_t idesc;
+    long long* dbg;  // optional timeline of CTA 0 (YR_PW_TC_DEBUG=1), else NULL
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -63,8 +68,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
-    // the suspend-time hint lets the hardware park the warp until the phase completes (it wakes
-    // on the arrival, ~60 cycles), so idle roles do not steal issue slots from working ones
+    // the suspend-time hint lets the hardware park the warp until the phase completes, so idle roles do
+    // not steal issue slots from working ones (measured: same or slightly better than the plain form)
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
@@ -77,7 +82,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // Bounded wait: a protocol bug traps (and fails the launch loudly) instead of hanging the GPU.
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int what) {
     for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
-        if (spins > (1u << 24)) {
+        if (spins > (1u << 17)) {
             printf("yoloret_b200 pw_tc: mbarrier wait timed out (role %d, block %d, thread %d)\n", what, blockIdx.x,
                    threadIdx.x);
             __trap();
@@ -108,6 +113,11 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -152,63 +162,175 @@ __host__ __device__ __forceinline__ float tf32_rna(float x) {
 #endif
 }
 
+// ---- barrier table (8 bytes each, at the end of the dynamic shared memory) -------------------
+constexpr int BAR_A_FULL = 0;                          // [MAX_A_STAGES]  TMA landed a raw A tile
+constexpr int BAR_A_CONV = BAR_A_FULL + MAX_A_STAGES;  // [MAX_A_STAGES]  converters wrote (hi, lo)
+constexpr int BAR_A_EMPTY = BAR_A_CONV + MAX_A_STAGES; // [MAX_A_STAGES]  MMAs that read the slot retired
+constexpr int BAR_L_EMPTY = BAR_A_EMPTY + MAX_A_STAGES;  // [MAX_L_SLOTS]
+constexpr int BAR_B_FULL = BAR_L_EMPTY + MAX_L_SLOTS;  // [MAX_B_SLOTS]
+constexpr int BAR_B_EMPTY = BAR_B_FULL + MAX_B_SLOTS;  // [MAX_B_SLOTS]
+constexpr int BAR_ACC_FULL = BAR_B_EMPTY + MAX_B_SLOTS;  // [MAX_ACC]
+constexpr int BAR_ACC_EMPTY = BAR_ACC_FULL + MAX_ACC;  // [MAX_ACC]
+constexpr int BAR_COUNT = BAR_ACC_EMPTY + MAX_ACC;
+static_assert(BAR_COUNT * 8 + 8 <= BAR_BYTES, "barrier table overflows its reservation");
+
+constexpr int DBG_EV = 256;  // events per role in the debug timeline
+__device__ __forceinline__ void dbg_mark(const Params& p, int role, uint32_t idx) {
+    if (p.dbg != nullptr && blockIdx.x == 0 && idx < DBG_EV) p.dbg[role * DBG_EV + idx] = clock64();
+}
+
+struct Ring {  // (slot, phase) cursor of a circular buffer; no div/mod on the hot path
+    uint32_t slot = 0, phase = 0;
+    __device__ __forceinline__ void advance(uint32_t n) {
+        if (++slot == n) { slot = 0; phase ^= 1u; }
+    }
+};
+
 // ---- epilogue: TMEM -> registers -> smem transpose -> bias / activation / residual -> 128-bit row stores
 // One warp owns TMEM lane quarter q (32 tile rows).  Per 32-column chunk: the accumulator row a lane
 // holds goes to smem as 8 STS.128 (row stride 36 floats: conflict-free per 8-lane phase), comes back
 // as LDS.128 with 8 lanes covering one row, and leaves as STG.128: 4 full 128-byte lines per store.
-constexpr int ACC_FULL_IDX = 3 * MAX_A_STAGES + 2 * MAX_B_SLOTS;
-
 template <int ACT, bool HAS_RES>
-__device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, uint32_t tmem_base, uint32_t bar0, int item0,
-                                              int item1, int q, int lane) {
+__device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, float* s_bias, uint32_t tmem_base,
+                                              uint32_t bar0, int item0, int item1, int q, int lane, int ewarp, int grp) {
     const int sub_r = lane >> 3;        // row within a 4-row group
     const int sub_c = (lane & 7) << 2;  // first of this lane's 4 columns within the chunk
     uint32_t it = 0;
+    Ring racc;
+    int nt = item0 / p.m_tiles, mt = item0 - nt * p.m_tiles;
+    int bias_nt = -1;
     for (int item = item0; item < item1; ++item, ++it) {
-        const int nt = item / p.m_tiles, mt = item - nt * p.m_tiles;
-        const uint32_t acc = it & 1;
-        mbar_wait(bar0 + 8u * (ACC_FULL_IDX + acc), (it >> 1) & 1, 6);
-        tc_fence_after();
+        if (p.nEpi == 2 && (int)(it & 1u) != grp) {  // the other epilogue group drains this tile
+            racc.advance(p.nAcc);
+            if (++mt == p.m_tiles) { mt = 0; ++nt; }
+            continue;
+        }
+        if (nt != bias_nt) {
+            // the n tile's bias lives in shared memory: a global load per 32-column chunk would put an L2
+            // round trip on the critical path of every chunk (named barrier 1+grp = the 4 warps of this epilogue group)
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+            for (int i = ewarp * 32 + lane; i < p.BN; i += 128) {
+                const int n = nt * p.BN + i;
+                s_bias[i] = n < p.N ? __ldg(p.bias + n) : 0.0f;
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+            bias_nt = nt;
+        }
+        const uint32_t acc = racc.slot;
         const int row0 = mt * BM + q * 32;
         const int ncols = min(p.BN, p.N - nt * p.BN);  // valid columns of this n tile (multiple of 8)
         const int rows = min(32, p.M - row0);          // valid rows of this warp's slab (may be <= 0)
         const uint32_t tsrc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.acc_stride;
+        bool waited = false;
         for (int c0 = 0; c0 < ncols; c0 += 32) {
+            const int c = c0 + sub_c;
+            const int n = nt * p.BN + c;
+            const bool col_ok = c < ncols;
+            float4 rv[8];
+            if (HAS_RES) {  // residual rows of this chunk: issued before the accumulator wait so DRAM latency overlaps
+                const float* rp = p.res + (size_t)(row0 + sub_r) * p.ld_res + n;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    rv[i] = (col_ok && sub_r + 4 * i < rows) ? ldg4(rp + (size_t)(4 * i) * p.ld_res) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (!waited) {
+                mbar_wait(bar0 + 8u * (BAR_ACC_FULL + acc), racc.phase, 6);
+                tc_fence_after();
+                waited = true;
+                if (ewarp == 0 && lane == 0) dbg_mark(p, 6, it);
+            }
             float v[32];
             tmem_ld32(tsrc + c0, v);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 *reinterpret_cast<float4*>(stg + lane * EPI_LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             __syncwarp();
-            const int c = c0 + sub_c;
-            if (c < ncols) {
-                const int n = nt * p.BN + c;
-                const float4 bv = ldg4(p.bias + n);
+            if (col_ok) {
+                const float4 bv = *reinterpret_cast<const float4*>(s_bias + c);
                 float* op = p.out + (size_t)(row0 + sub_r) * p.ld_out + n;
-                const float* rp = HAS_RES ? p.res + (size_t)(row0 + sub_r) * p.ld_res + n : nullptr;
                 const float* sp = stg + sub_r * EPI_LD + sub_c;
-                const size_t ostep = (size_t)4 * p.ld_out, rstep = (size_t)4 * p.ld_res;
-#pragma unroll 4
-                for (int r = sub_r; r < rows; r += 4) {
-                    float4 x = *reinterpret_cast<const float4*>(sp);
-                    x.x = apply_act<ACT>(x.x + bv.x);
-                    x.y = apply_act<ACT>(x.y + bv.y);
-                    x.z = apply_act<ACT>(x.z + bv.z);
-                    x.w = apply_act<ACT>(x.w + bv.w);
-                    if (HAS_RES) {
-                        const float4 rv = ldg4(rp);
-                        x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w;
-                        rp += rstep;
+                const size_t ostep = (size_t)4 * p.ld_out;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (sub_r + 4 * i < rows) {
+                        float4 x = *reinterpret_cast<const float4*>(sp + (4 * i) * EPI_LD);
+                        x.x = apply_act<ACT>(x.x + bv.x);
+                        x.y = apply_act<ACT>(x.y + bv.y);
+                        x.z = apply_act<ACT>(x.z + bv.z);
+                        x.w = apply_act<ACT>(x.w + bv.w);
+                        if (HAS_RES) { x.x += rv[i].x; x.y += rv[i].y; x.z += rv[i].z; x.w += rv[i].w; }
+                        st4(op + (size_t)i * ostep, x);
                     }
-                    st4(op, x);
-                    op += ostep;
-                    sp += 4 * EPI_LD;
                 }
             }
             __syncwarp();
         }
+        if (!waited) {  // no valid columns (cannot happen for a well-formed tiling); keep the protocol in step
+            mbar_wait(bar0 + 8u * (BAR_ACC_FULL + acc), racc.phase, 6);
+            tc_fence_after();
+        }
         tc_fence_before();
-        mbar_arrive(bar0 + 8u * (ACC_FULL_IDX + 2 + acc));
+        mbar_arrive(bar0 + 8u * (BAR_ACC_EMPTY + acc));
+        if (ewarp == 0 && lane == 0) dbg_mark(p, 7, it);
+        racc.advance(p.nAcc);
+        if (++mt == p.m_tiles) { mt = 0; ++nt; }
+    }
+}
+
+// ---- converters: raw fp32 A tile -> (hi, lo) TF32 tiles; the SE gate is folded in here -------------
+// 8 warps; each thread owns 4 of the tile's 1024 16-byte chunks.  hi overwrites the raw tile in place
+// (an elementwise map keeps the TMA swizzle), lo goes to a slot of the short lo ring.
+template <bool HAS_SCALE>
+__device__ __forceinline__ void converter_loop(const Params& p, uint8_t* gbase, uint32_t a_off, uint32_t l_off,
+                                               uint32_t bar0, int item0, int item1, int ct, int grp) {
+    Ring ra, rl;
+    uint32_t dq = 0;
+    int mt = item0 % p.m_tiles;
+    for (int item = item0; item < item1; ++item) {
+        for (int kb = 0; kb < p.KB; ++kb, ++dq) {
+            if ((int)(dq & 1u) == grp) {
+                mbar_wait(bar0 + 8u * (BAR_A_FULL + ra.slot), ra.phase, 5);
+                if (ct == 0) dbg_mark(p, 1, dq);
+                mbar_wait(bar0 + 8u * (BAR_L_EMPTY + rl.slot), rl.phase ^ 1u, 7);
+                if (ct == 0) dbg_mark(p, 2, dq);
+                float4* hi = reinterpret_cast<float4*>(gbase + a_off + ra.slot * (uint32_t)A_TILE_BYTES);
+                float4* lo = reinterpret_cast<float4*>(gbase + l_off + rl.slot * (uint32_t)A_TILE_BYTES);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float4 v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = hi[ct + (half * 4 + j) * 128];
+                    if (HAS_SCALE) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int i = ct + (half * 4 + j) * 128;
+                            const int r = i >> 3;
+                            const int k = kb * BK + (((i & 7) ^ (r & 7)) << 2);  // undo the 128B swizzle
+                            const int row = mt * BM + r;
+                            if (k < p.K && row < p.M) {
+                                const float4 g = ldg4(p.scale + (size_t)(row / p.rows_per_img) * p.K + k);
+                                v[j].x *= g.x; v[j].y *= g.y; v[j].z *= g.z; v[j].w *= g.w;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float4 h, l;
+                        h.x = tf32_rna(v[j].x); h.y = tf32_rna(v[j].y); h.z = tf32_rna(v[j].z); h.w = tf32_rna(v[j].w);
+                        l.x = tf32_rna(v[j].x - h.x); l.y = tf32_rna(v[j].y - h.y);
+                        l.z = tf32_rna(v[j].z - h.z); l.w = tf32_rna(v[j].w - h.w);
+                        hi[ct + (half * 4 + j) * 128] = h;
+                        lo[ct + (half * 4 + j) * 128] = l;
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(bar0 + 8u * (BAR_A_CONV + ra.slot));
+                if (ct == 0) dbg_mark(p, 3, dq);
+            }
+            ra.advance(p.nA);
+            rl.advance(p.nL);
+        }
+        if (++mt == p.m_tiles) mt = 0;
     }
 }
 
@@ -216,39 +338,33 @@ __device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, uint3
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: [A stages: (hi 16K | lo 16K) x nA][B slots: (hi | lo) x nB][epilogue transpose][barriers]
+    // carve: [A ring: nA x 16K raw->hi][lo ring: nL x 16K][B slots: (hi | lo) x nB][epilogue transpose][barriers]
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t b_slot_bytes = 2u * p.BN * 128u;
-    const uint32_t a_off = 0, b_off = a_off + p.nA * 2u * A_TILE_BYTES;
+    const uint32_t a_off = 0, l_off = a_off + p.nA * (uint32_t)A_TILE_BYTES;
+    const uint32_t b_off = l_off + p.nL * (uint32_t)A_TILE_BYTES;
     const uint32_t epi_off = b_off + p.nB * b_slot_bytes;
-    const uint32_t bar_off = epi_off + EPI_BYTES;
-    // barrier slots (8 bytes each)
+    const uint32_t bar_off = epi_off + p.nEpi * (uint32_t)EPI_GROUP_BYTES;
     const uint32_t bar0 = base + bar_off;
-    auto a_full = [&](int s) { return bar0 + 8u * s; };
-    auto a_conv = [&](int s) { return bar0 + 8u * (MAX_A_STAGES + s); };
-    auto a_empty = [&](int s) { return bar0 + 8u * (2 * MAX_A_STAGES + s); };
-    auto b_full = [&](int s) { return bar0 + 8u * (3 * MAX_A_STAGES + s); };
-    auto b_empty = [&](int s) { return bar0 + 8u * (3 * MAX_A_STAGES + MAX_B_SLOTS + s); };
-    auto acc_full = [&](int s) { return bar0 + 8u * (3 * MAX_A_STAGES + 2 * MAX_B_SLOTS + s); };
-    auto acc_empty = [&](int s) { return bar0 + 8u * (3 * MAX_A_STAGES + 2 * MAX_B_SLOTS + 2 + s); };
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gbase + bar_off + 8u * (3 * MAX_A_STAGES + 2 * MAX_B_SLOTS + 4));
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gbase + bar_off + 8u * BAR_COUNT);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.nA; ++s) {
-            mbar_init(a_full(s), 1);
-            mbar_init(a_conv(s), 128);
-            mbar_init(a_empty(s), 1);
+            mbar_init(bar0 + 8u * (BAR_A_FULL + s), 1);
+            mbar_init(bar0 + 8u * (BAR_A_CONV + s), NUM_CONVERTERS / 2);
+            mbar_init(bar0 + 8u * (BAR_A_EMPTY + s), 1);
         }
+        for (int s = 0; s < p.nL; ++s) mbar_init(bar0 + 8u * (BAR_L_EMPTY + s), 1);
         for (int s = 0; s < p.nB; ++s) {
-            mbar_init(b_full(s), 1);
-            mbar_init(b_empty(s), 1);
+            mbar_init(bar0 + 8u * (BAR_B_FULL + s), 1);
+            mbar_init(bar0 + 8u * (BAR_B_EMPTY + s), 1);
         }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(acc_full(s), 1);
-            mbar_init(acc_empty(s), 128);
+        for (int s = 0; s < p.nAcc; ++s) {
+            mbar_init(bar0 + 8u * (BAR_ACC_FULL + s), 1);
+            mbar_init(bar0 + 8u * (BAR_ACC_EMPTY + s), 128);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -270,120 +386,107 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
         // ===== producer =====
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-            uint32_t aq = 0, bq = 0;
+            Ring ra, rb;
             bool b_loaded = false;
+            uint32_t dq = 0;
+            int nt = item0 / p.m_tiles, mt = item0 - nt * p.m_tiles;
             for (int item = item0; item < item1; ++item) {
-                const int nt = item / p.m_tiles, mt = item - nt * p.m_tiles;
+                const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wp) + (size_t)nt * p.KB * b_slot_bytes;
                 for (int kb = 0; kb < p.KB; ++kb) {
                     if (!(p.resident && b_loaded)) {
-                        const uint32_t slot = bq % p.nB;
-                        mbar_wait(b_empty(slot), ((bq / p.nB) & 1) ^ 1, 0);
-                        mbar_expect_tx(b_full(slot), b_slot_bytes);
-                        bulk_load(base + b_off + slot * b_slot_bytes,
-                                  reinterpret_cast<const uint8_t*>(p.wp) + ((size_t)nt * p.KB + kb) * b_slot_bytes,
-                                  b_slot_bytes, b_full(slot));
-                        ++bq;
+                        mbar_wait(bar0 + 8u * (BAR_B_EMPTY + rb.slot), rb.phase ^ 1u, 0);
+                        mbar_expect_tx(bar0 + 8u * (BAR_B_FULL + rb.slot), b_slot_bytes);
+                        bulk_load(base + b_off + rb.slot * b_slot_bytes, wsrc + (size_t)kb * b_slot_bytes, b_slot_bytes,
+                                  bar0 + 8u * (BAR_B_FULL + rb.slot));
+                        rb.advance(p.nB);
                     }
-                    const uint32_t st = aq % p.nA;
-                    mbar_wait(a_empty(st), ((aq / p.nA) & 1) ^ 1, 1);
-                    mbar_expect_tx(a_full(st), A_TILE_BYTES);
-                    tma_load_2d(base + a_off + st * 2u * A_TILE_BYTES, &tmA, a_full(st), kb * BK, mt * BM);
-                    ++aq;
+                    mbar_wait(bar0 + 8u * (BAR_A_EMPTY + ra.slot), ra.phase ^ 1u, 1);
+                    mbar_expect_tx(bar0 + 8u * (BAR_A_FULL + ra.slot), A_TILE_BYTES);
+                    tma_load_2d(base + a_off + ra.slot * (uint32_t)A_TILE_BYTES, &tmA, bar0 + 8u * (BAR_A_FULL + ra.slot),
+                                kb * BK, mt * BM);
+                    dbg_mark(p, 0, dq++);
+                    ra.advance(p.nA);
                 }
                 b_loaded = true;
+                if (++mt == p.m_tiles) { mt = 0; ++nt; }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            uint32_t aq = 0, bq = 0, it = 0;
-            for (int item = item0; item < item1; ++item, ++it) {
-                const uint32_t acc = it & 1;
-                mbar_wait(acc_empty(acc), ((it >> 1) & 1) ^ 1, 2);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.acc_stride;
-                for (int kb = 0; kb < p.KB; ++kb) {
-                    uint32_t slot;
-                    if (p.resident) {
-                        slot = kb;
-                        mbar_wait(b_full(slot), 0, 3);
-                    } else {
-                        slot = bq % p.nB;
-                        mbar_wait(b_full(slot), (bq / p.nB) & 1, 3);
-                        ++bq;
-                    }
-                    const uint32_t st = aq % p.nA;
-                    mbar_wait(a_conv(st), (aq / p.nA) & 1, 4);
-                    ++aq;
-                    tc_fence_after();
-                    const uint32_t a_hi = base + a_off + st * 2u * A_TILE_BYTES, a_lo = a_hi + A_TILE_BYTES;
-                    const uint32_t b_hi = base + b_off + slot * b_slot_bytes, b_lo = b_hi + p.BN * 128u;
-                    const int ksteps = min(BK, p.K - kb * BK + 7) / 8;  // skip all-zero K steps of the tail
-                    for (int k8 = 0; k8 < ksteps; ++k8) {
-                        const uint64_t dah = make_desc_sw128(a_hi + k8 * 32), dal = make_desc_sw128(a_lo + k8 * 32);
-                        const uint64_t dbh = make_desc_sw128(b_hi + k8 * 32), dbl = make_desc_sw128(b_lo + k8 * 32);
-                        umma_tf32(d_tmem, dal, dbh, p.idesc, (kb | k8) ? 1u : 0u);  // small terms first
-                        umma_tf32(d_tmem, dah, dbl, p.idesc, 1u);
-                        umma_tf32(d_tmem, dah, dbh, p.idesc, 1u);
-                    }
-                    umma_commit(a_empty(st));
-                    if (!p.resident) umma_commit(b_empty(slot));
-                }
-                umma_commit(acc_full(acc));
-            }
-        }
-        __syncwarp();
-    } else if (warp < 6) {
-        // ===== converters: raw fp32 tile -> (hi, lo) TF32 tiles, in place; SE gate folded in =====
-        const int ct = threadIdx.x - 64;  // 0..127
-        uint32_t aq = 0;
+        // ===== MMA issuer: the whole warp runs the loop converged (addresses stay in uniform registers);
+        // one elected lane issues the tcgen05 instructions =====
+        Ring ra, rl, rb, racc;
+        uint32_t dq = 0;
+        // descriptors differ only in the 14-bit start-address field: build one, then add (bytes >> 4)
+        const uint64_t desc0 = make_desc_sw128(base);
+        const int k_tail = (p.K - (p.KB - 1) * BK + 7) / 8;  // 8-wide K steps of the last k-block
         for (int item = item0; item < item1; ++item) {
-            const int mt = item % p.m_tiles;
-            for (int kb = 0; kb < p.KB; ++kb, ++aq) {
-                const uint32_t st = aq % p.nA;
-                mbar_wait(a_full(st), (aq / p.nA) & 1, 5);
-                float4* hi = reinterpret_cast<float4*>(gbase + a_off + st * 2u * A_TILE_BYTES);
-                float4* lo = reinterpret_cast<float4*>(gbase + a_off + st * 2u * A_TILE_BYTES + A_TILE_BYTES);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int i = ct + j * 128;  // 16-byte chunk index inside the tile
-                    float4 v = hi[i];
-                    if (p.scale != nullptr) {
-                        const int r = i >> 3;
-                        const int k = kb * BK + (((i & 7) ^ (r & 7)) << 2);  // undo the 128B swizzle
-                        const int row = mt * BM + r;
-                        if (k < p.K && row < p.M) {
-                            const float4 g = ldg4(p.scale + (size_t)(row / p.rows_per_img) * p.K + k);
-                            v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
-                        }
-                    }
-                    float4 h, l;
-                    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-                    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y);
-                    l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-                    hi[i] = h;
-                    lo[i] = l;
+            const uint32_t acc = racc.slot;
+            mbar_wait(bar0 + 8u * (BAR_ACC_EMPTY + acc), racc.phase ^ 1u, 2);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.acc_stride;
+            for (int kb = 0; kb < p.KB; ++kb) {
+                uint32_t slot;
+                if (p.resident) {
+                    slot = kb;
+                    mbar_wait(bar0 + 8u * (BAR_B_FULL + slot), 0, 3);
+                } else {
+                    slot = rb.slot;
+                    mbar_wait(bar0 + 8u * (BAR_B_FULL + slot), rb.phase, 3);
+                    rb.advance(p.nB);
                 }
-                fence_proxy_async();
-                mbar_arrive(a_conv(st));
+                mbar_wait(bar0 + 8u * (BAR_A_CONV + ra.slot), ra.phase, 4);
+                tc_fence_after();
+                if (lane == 0) dbg_mark(p, 4, dq);
+                const uint64_t dah = desc0 + ((a_off + ra.slot * (uint32_t)A_TILE_BYTES) >> 4);
+                const uint64_t dal = desc0 + ((l_off + rl.slot * (uint32_t)A_TILE_BYTES) >> 4);
+                const uint64_t dbh = desc0 + ((b_off + slot * b_slot_bytes) >> 4);
+                const uint64_t dbl = dbh + ((p.BN * 128u) >> 4);
+                const int ksteps = (kb == p.KB - 1) ? k_tail : BK / 8;  // skip all-zero K steps of the tail
+                if (elect_one()) {
+                    for (int k8 = 0; k8 < ksteps; ++k8) {
+                        const uint64_t ko = (uint64_t)(k8 * 2);  // 32 bytes per 8-wide TF32 K step
+                        umma_tf32(d_tmem, dal + ko, dbh + ko, p.idesc, (kb | k8) ? 1u : 0u);  // small terms first
+                        umma_tf32(d_tmem, dah + ko, dbl + ko, p.idesc, 1u);
+                        umma_tf32(d_tmem, dah + ko, dbh + ko, p.idesc, 1u);
+                    }
+                    umma_commit(bar0 + 8u * (BAR_A_EMPTY + ra.slot));
+                    umma_commit(bar0 + 8u * (BAR_L_EMPTY + rl.slot));
+                    if (!p.resident) umma_commit(bar0 + 8u * (BAR_B_EMPTY + slot));
+                    if (kb == p.KB - 1) umma_commit(bar0 + 8u * (BAR_ACC_FULL + acc));
+                }
+                __syncwarp();
+                if (lane == 0) dbg_mark(p, 5, dq);
+                ++dq;
+                ra.advance(p.nA);
+                rl.advance(p.nL);
             }
+            racc.advance(p.nAcc);
         }
+    } else if (warp < 2 + NUM_CONVERTERS / 32) {
+        const int ct = (threadIdx.x - 64) & 127, cg = (threadIdx.x - 64) >> 7;  // thread within group, group
+        if (p.scale != nullptr) converter_loop<true>(p, gbase, a_off, l_off, bar0, item0, item1, ct, cg);
+        else converter_loop<false>(p, gbase, a_off, l_off, bar0, item0, item1, ct, cg);
     } else {
         // ===== epilogue =====
-        float* stg = reinterpret_cast<float*>(gbase + epi_off) + (warp - 6) * 32 * EPI_LD;
+        const int ew8 = warp - (2 + NUM_CONVERTERS / 32);  // 0..7
+        const int ew = ew8 & 3, eg = ew8 >> 2;             // warp within its group, group
+        float* stg = reinterpret_cast<float*>(gbase + epi_off + eg * EPI_GROUP_BYTES) + ew * 32 * EPI_LD;
+        float* s_bias = reinterpret_cast<float*>(gbase + epi_off + eg * EPI_GROUP_BYTES + 4 * 32 * EPI_LD * 4);
+        if (eg < p.nEpi) {
         const bool has_res = p.res != nullptr;
         switch (p.act) {
             case YR_ACT_RELU6:
-                if (has_res) epilogue_loop<YR_ACT_RELU6, true>(p, stg, tmem_base, bar0, item0, item1, warp & 3, lane);
-                else epilogue_loop<YR_ACT_RELU6, false>(p, stg, tmem_base, bar0, item0, item1, warp & 3, lane);
+                if (has_res) epilogue_loop<YR_ACT_RELU6, true>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else epilogue_loop<YR_ACT_RELU6, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
                 break;
             case YR_ACT_SWISH:
-                if (has_res) epilogue_loop<YR_ACT_SWISH, true>(p, stg, tmem_base, bar0, item0, item1, warp & 3, lane);
-                else epilogue_loop<YR_ACT_SWISH, false>(p, stg, tmem_base, bar0, item0, item1, warp & 3, lane);
+                if (has_res) epilogue_loop<YR_ACT_SWISH, true>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else epilogue_loop<YR_ACT_SWISH, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
                 break;
             default:
-                if (has_res) epilogue_loop<YR_ACT_NONE, true>(p, stg, tmem_base, bar0, item0, item1, warp & 3, lane);
-                else epilogue_loop<YR_ACT_NONE, false>(p, stg, tmem_base, bar0, item0, item1, warp & 3, lane);
+                if (has_res) epilogue_loop<YR_ACT_NONE, true>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else epilogue_loop<YR_ACT_NONE, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+        }
         }
     }
 
@@ -419,7 +522,7 @@ __global__ void pack_kernel(const float* __restrict__ w, int K, int N, int BN, i
 
 // ---- host side ----------------------------------------------------------------------------------
 struct Tiling {
-    int BN, n_tiles, KB, nA, nB, resident, tmem_cols, acc_stride;
+    int BN, n_tiles, KB, nA, nL, nB, nAcc, nEpi, resident, tmem_cols, acc_stride;
     size_t smem;
 };
 
@@ -435,31 +538,52 @@ static bool make_tiling(int K, int N, Tiling& t) {
     if (t.BN < 16) t.BN = 16;
     t.KB = (K + BK - 1) / BK;
     const long long slot = 2ll * t.BN * 128;
-    const long long fixed = 1024 /*alignment slack*/ + EPI_BYTES + 1024 /*barriers*/;
-    const long long avail = SMEM_LIMIT - fixed;
-    const long long a_stage = 2ll * A_TILE_BYTES;
-    if (t.n_tiles == 1 && t.KB <= MAX_B_SLOTS && t.KB * slot + 3 * a_stage <= avail) {
-        t.resident = 1;
-        t.nB = t.KB;
-    } else {
+    const long long tile = A_TILE_BYTES;
+    bool ok = false;
+    long long fixed = 0;
+    // Resident weights (the common case for the huge-M layers): two epilogue groups, 4 lo slots, the rest
+    // of shared memory is the raw A ring.  Streamed weights: one epilogue group and 2 lo slots leave room
+    // for one more weight slot, which is what the MMA waits on there.
+    {
+        t.nEpi = 2;
+        t.nL = 4;
+        fixed = 1024 /*alignment slack*/ + (long long)t.nEpi * EPI_GROUP_BYTES + BAR_BYTES;
+        const long long avail = SMEM_LIMIT - fixed;
+        if (t.n_tiles == 1 && t.KB <= MAX_B_SLOTS && t.KB * slot + (4 + t.nL) * tile <= avail) {
+            t.resident = 1;
+            t.nB = t.KB;
+            long long na = (avail - t.nB * slot - t.nL * tile) / tile;
+            t.nA = (int)(na > MAX_A_STAGES ? MAX_A_STAGES : na);
+            ok = true;
+        }
+    }
+    if (!ok) {
+        t.nEpi = 1;
+        t.nL = 2;
         t.resident = 0;
-        long long nb = (avail / 2) / slot;
-        if (nb < 2) nb = 2;
+        fixed = 1024 + (long long)t.nEpi * EPI_GROUP_BYTES + BAR_BYTES;
+        const long long avail = SMEM_LIMIT - fixed;
+        long long nb = (avail - (t.nL + 3) * tile) / slot;  // keep at least 3 raw A slots
         if (nb > 4) nb = 4;
         if (nb > t.KB) nb = t.KB;
+        if (nb < 2) nb = 2;
         t.nB = (int)nb;
         if (t.nB >= t.KB && t.n_tiles == 1 && t.KB <= MAX_B_SLOTS) t.resident = 1;
+        long long na = (avail - t.nB * slot - t.nL * tile) / tile;
+        if (na > MAX_A_STAGES) na = MAX_A_STAGES;
+        t.nA = (int)na;
+        ok = na >= 2;
     }
-    long long na = (avail - t.nB * slot) / a_stage;
-    if (na > MAX_A_STAGES) na = MAX_A_STAGES;
-    if (na < 2) return false;
-    t.nA = (int)na;
+    if (!ok) return false;
     t.acc_stride = (t.BN + 31) / 32 * 32;  // the epilogue reads TMEM in 32-column chunks
+    t.nAcc = 512 / t.acc_stride;  // a deep accumulator ring hides the MMA -> epilogue -> MMA round trip
+    if (t.nAcc > MAX_ACC) t.nAcc = MAX_ACC;
+    if (t.nAcc < 2) return false;
     int cols = 32;
-    while (cols < 2 * t.acc_stride) cols *= 2;
+    while (cols < t.nAcc * t.acc_stride) cols *= 2;
     if (cols > 512) return false;
     t.tmem_cols = cols;
-    t.smem = (size_t)(fixed + t.nA * a_stage + t.nB * slot);
+    t.smem = (size_t)(fixed + (t.nA + t.nL) * tile + t.nB * slot);
     return t.smem <= (size_t)SMEM_LIMIT;
 }
 
@@ -544,6 +668,9 @@ int launch_pw_tc(const yr_op& op, cudaStream_t s) {
     p.rows_per_img = op.H * op.W;
     p.act = op.act;
     p.nA = t.nA;
+    p.nL = t.nL;
+    p.nAcc = t.nAcc;
+    p.nEpi = t.nEpi;
     p.nB = t.nB;
     p.resident = t.resident;
     p.tmem_cols = t.tmem_cols;
@@ -563,8 +690,31 @@ int launch_pw_tc(const yr_op& op, cudaStream_t s) {
         }
         attr_set = true;
     }
+    p.dbg = nullptr;
+    static const bool debug = getenv("YR_PW_TC_DEBUG") != nullptr;  // developer aid only: timeline of CTA 0
+    if (debug) {
+        static long long* dbuf = nullptr;
+        if (!dbuf) cudaMalloc(&dbuf, 8 * tc::DBG_EV * sizeof(long long));
+        cudaMemsetAsync(dbuf, 0, 8 * tc::DBG_EV * sizeof(long long), s);
+        p.dbg = dbuf;
+    }
     tc::pw_tc_kernel<<<grid, tc::NUM_THREADS, t.smem, s>>>(tm, p);
     YR_CHECK_LAUNCH("pw_tc");
+    if (debug) {
+        static long long h[8 * tc::DBG_EV];
+        cudaStreamSynchronize(s);
+        cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        const char* names[8] = {"tma_issue", "a_full_seen", "lo_empty_seen", "conv_done", "mma_start", "mma_issued",
+                                "acc_full_seen", "epi_done"};
+        long long t0 = h[0];
+        fprintf(stderr, "pw_tc timeline K=%d N=%d KB=%d nA=%d nL=%d nB=%d resident=%d items/cta=%d (cycles since first TMA)\n",
+                p.K, p.N, p.KB, p.nA, p.nL, p.nB, p.resident, p.items_per_cta);
+        for (int r = 0; r < 8; ++r) {
+            fprintf(stderr, "%-14s", names[r]);
+            for (int i = 0; i < 40 && h[r * tc::DBG_EV + i]; ++i) fprintf(stderr, " %6lld", h[r * tc::DBG_EV + i] - t0);
+            fprintf(stderr, "\n");
+        }
+    }
     return YR_OK;
 }
 
