@@ -235,93 +235,87 @@ int launch_resample(const yr_op& op, cudaStream_t s) {
 // conv-then-pool for b3, pool-then-conv for b4, adds left to right, as the reference.
 // One CTA = RF_PIX consecutive output pixels of a row; inputs staged in shared memory.
 // ---------------------------------------------------------------------------------
-constexpr int RF_PIX = 8;
-
-__global__ void rfcr_kernel(const float* __restrict__ b1, int ld1, int K1, const float* __restrict__ b2, int ld2, int K2,
-                            const float* __restrict__ b3, int ld3, int K3, const float* __restrict__ b4, int ld4, int K4,
-                            const float* __restrict__ wgt, const float* __restrict__ alpha, float* __restrict__ out,
-                            int ld_out, int H, int W, int N) {
+// One CTA = one output row: the stacked 1x1 kernels (K1+K2+K3+K4 rows of N) and the row's inputs are
+// staged in shared memory once, then every thread owns (pixel, 4 output channels) items.
+__global__ void __launch_bounds__(256)
+rfcr_kernel(const float* __restrict__ b1, int ld1, int K1, const float* __restrict__ b2, int ld2, int K2,
+            const float* __restrict__ b3, int ld3, int K3, const float* __restrict__ b4, int ld4, int K4,
+            const float* __restrict__ wgt, const float* __restrict__ alpha, float* __restrict__ out, int ld_out, int H,
+            int W, int N) {
     extern __shared__ __align__(16) float sm[];
-    float* s1 = sm;                          // [RF_PIX/2][K1]
-    float* s2 = s1 + (RF_PIX / 2) * K1;      // [RF_PIX][K2]
-    float* s3 = s2 + RF_PIX * K2;            // [RF_PIX][4][K3]
-    float* s4 = s3 + RF_PIX * 4 * K3;        // [RF_PIX][K4]
-    const int w0 = blockIdx.x * RF_PIX;      // even
-    const int h = blockIdx.y;
-    const int b = blockIdx.z;
-    const int H1 = H >> 1, W1 = W >> 1;
+    const int KT = K1 + K2 + K3 + K4;
+    const int W1 = W >> 1, H1 = H >> 1;
+    float* sw = sm;                      // [KT][N]
+    float* s1 = sw + (size_t)KT * N;     // [W1][K1]
+    float* s2 = s1 + W1 * K1;            // [W][K2]
+    float* s3 = s2 + W * K2;             // [W][4][K3]
+    float* s4 = s3 + W * 4 * K3;         // [W][K4]   (4x4 max-pooled b4)
+    const int h = blockIdx.x, b = blockIdx.y;
     const int tid = threadIdx.x, nt = blockDim.x;
 
-    for (int i = tid; i < (RF_PIX / 2) * (K1 / 4); i += nt) {
+    for (int i = tid; i < KT * N / 4; i += nt) st4(sw + i * 4, ldg4(wgt + (size_t)i * 4));
+    for (int i = tid; i < W1 * (K1 / 4); i += nt) {
         const int p = i / (K1 / 4), k = (i % (K1 / 4)) * 4;
-        const int w1 = (w0 >> 1) + p;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (w1 < W1) v = ldg4(b1 + (((size_t)b * H1 + (h >> 1)) * W1 + w1) * ld1 + k);
-        st4(s1 + p * K1 + k, v);
+        st4(s1 + p * K1 + k, ldg4(b1 + (((size_t)b * H1 + (h >> 1)) * W1 + p) * ld1 + k));
     }
-    for (int i = tid; i < RF_PIX * (K2 / 4); i += nt) {
+    for (int i = tid; i < W * (K2 / 4); i += nt) {
         const int p = i / (K2 / 4), k = (i % (K2 / 4)) * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (w0 + p < W) v = ldg4(b2 + (((size_t)b * H + h) * W + w0 + p) * ld2 + k);
-        st4(s2 + p * K2 + k, v);
+        st4(s2 + p * K2 + k, ldg4(b2 + (((size_t)b * H + h) * W + p) * ld2 + k));
     }
-    for (int i = tid; i < RF_PIX * 4 * (K3 / 4); i += nt) {
+    for (int i = tid; i < W * 4 * (K3 / 4); i += nt) {
         const int k = (i % (K3 / 4)) * 4;
         const int q = (i / (K3 / 4)) % 4, p = i / (K3 / 4) / 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (w0 + p < W)
-            v = ldg4(b3 + (((size_t)b * 2 * H + 2 * h + (q >> 1)) * (2 * W) + 2 * (w0 + p) + (q & 1)) * ld3 + k);
-        st4(s3 + (p * 4 + q) * K3 + k, v);
+        st4(s3 + (p * 4 + q) * K3 + k,
+            ldg4(b3 + (((size_t)b * 2 * H + 2 * h + (q >> 1)) * (2 * W) + 2 * p + (q & 1)) * ld3 + k));
     }
-    for (int i = tid; i < RF_PIX * (K4 / 4); i += nt) {
+    for (int i = tid; i < W * (K4 / 4); i += nt) {
         const int p = i / (K4 / 4), k = (i % (K4 / 4)) * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (w0 + p < W) {
-            const float* base = b4 + (((size_t)b * 4 * H + 4 * h) * (4 * W) + 4 * (w0 + p)) * ld4 + k;
-            v = ldg4(base);
+        const float* base = b4 + (((size_t)b * 4 * H + 4 * h) * (4 * W) + 4 * p) * ld4 + k;
+        float4 v = ldg4(base);
 #pragma unroll
-            for (int y = 0; y < 4; ++y)
+        for (int y = 0; y < 4; ++y)
 #pragma unroll
-                for (int x = 0; x < 4; ++x)
-                    if (y | x) v = max4(v, ldg4(base + ((size_t)y * 4 * W + x) * ld4));
-        }
+            for (int x = 0; x < 4; ++x)
+                if (y | x) v = max4(v, ldg4(base + ((size_t)y * 4 * W + x) * ld4));
         st4(s4 + p * K4 + k, v);
     }
     __syncthreads();
 
     const int N4 = N >> 2;
-    const int p = tid / N4, n = (tid % N4) * 4;
-    if (p >= RF_PIX || w0 + p >= W) return;
-    auto dot = [&](const float* x, const float* wk, int K) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int k = 0; k < K; ++k) {
-            const float xv = x[k];
-            const float4 wv = ldg4(wk + (size_t)k * N + n);
-            a.x = fmaf(xv, wv.x, a.x);
-            a.y = fmaf(xv, wv.y, a.y);
-            a.z = fmaf(xv, wv.z, a.z);
-            a.w = fmaf(xv, wv.w, a.w);
-        }
-        return a;
-    };
-    const float* w1p = wgt;
+    const float a0 = __ldg(alpha), a1 = __ldg(alpha + 1), a2 = __ldg(alpha + 2), a3 = __ldg(alpha + 3);
+    const float* w1p = sw;
     const float* w2p = w1p + (size_t)K1 * N;
     const float* w3p = w2p + (size_t)K2 * N;
     const float* w4p = w3p + (size_t)K3 * N;
-    const float4 c1 = dot(s1 + (p >> 1) * K1, w1p, K1);
-    const float4 c2 = dot(s2 + p * K2, w2p, K2);
-    float4 c3 = dot(s3 + (p * 4 + 0) * K3, w3p, K3);
-    c3 = max4(c3, dot(s3 + (p * 4 + 1) * K3, w3p, K3));
-    c3 = max4(c3, dot(s3 + (p * 4 + 2) * K3, w3p, K3));
-    c3 = max4(c3, dot(s3 + (p * 4 + 3) * K3, w3p, K3));
-    const float4 c4 = dot(s4 + p * K4, w4p, K4);
-    const float a0 = __ldg(alpha), a1 = __ldg(alpha + 1), a2 = __ldg(alpha + 2), a3 = __ldg(alpha + 3);
-    float4 v;  // ((a0*x0 + a1*x1) + a2*x2) + a3*x3, no FMA contraction across the adds
-    v.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a0, c1.x), __fmul_rn(a1, c2.x)), __fmul_rn(a2, c3.x)), __fmul_rn(a3, c4.x));
-    v.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a0, c1.y), __fmul_rn(a1, c2.y)), __fmul_rn(a2, c3.y)), __fmul_rn(a3, c4.y));
-    v.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a0, c1.z), __fmul_rn(a1, c2.z)), __fmul_rn(a2, c3.z)), __fmul_rn(a3, c4.z));
-    v.w = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a0, c1.w), __fmul_rn(a1, c2.w)), __fmul_rn(a2, c3.w)), __fmul_rn(a3, c4.w));
-    st4(out + (((size_t)b * H + h) * W + w0 + p) * ld_out + n, v);
+    for (int item = tid; item < W * N4; item += nt) {
+        const int p = item / N4, n = (item % N4) * 4;
+        auto dot = [&](const float* x, const float* wk, int K) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int k = 0; k < K; ++k) {
+                const float xv = x[k];
+                const float4 wv = *reinterpret_cast<const float4*>(wk + (size_t)k * N + n);
+                a.x = fmaf(xv, wv.x, a.x);
+                a.y = fmaf(xv, wv.y, a.y);
+                a.z = fmaf(xv, wv.z, a.z);
+                a.w = fmaf(xv, wv.w, a.w);
+            }
+            return a;
+        };
+        const float4 c1 = dot(s1 + (p >> 1) * K1, w1p, K1);
+        const float4 c2 = dot(s2 + p * K2, w2p, K2);
+        float4 c3 = dot(s3 + (p * 4 + 0) * K3, w3p, K3);
+        c3 = max4(c3, dot(s3 + (p * 4 + 1) * K3, w3p, K3));
+        c3 = max4(c3, dot(s3 + (p * 4 + 2) * K3, w3p, K3));
+        c3 = max4(c3, dot(s3 + (p * 4 + 3) * K3, w3p, K3));
+        const float4 c4 = dot(s4 + p * K4, w4p, K4);
+        float4 v;  // ((a0*x0 + a1*x1) + a2*x2) + a3*x3, no FMA contraction across the adds
+        v.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a0, c1.x), __fmul_rn(a1, c2.x)), __fmul_rn(a2, c3.x)), __fmul_rn(a3, c4.x));
+        v.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a0, c1.y), __fmul_rn(a1, c2.y)), __fmul_rn(a2, c3.y)), __fmul_rn(a3, c4.y));
+        v.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a0, c1.z), __fmul_rn(a1, c2.z)), __fmul_rn(a2, c3.z)), __fmul_rn(a3, c4.z));
+        v.w = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a0, c1.w), __fmul_rn(a1, c2.w)), __fmul_rn(a2, c3.w)), __fmul_rn(a3, c4.w));
+        st4(out + (((size_t)b * H + h) * W + p) * ld_out + n, v);
+    }
 }
 
 int launch_rfcr(const yr_op& op, cudaStream_t s) {
@@ -329,14 +323,20 @@ int launch_rfcr(const yr_op& op, cudaStream_t s) {
     const int K1 = op.C, K2 = op.K2, K3 = op.K3, K4 = op.K4, N = op.N;
     YR_CHECK_ARG(K1 % 4 == 0 && K2 % 4 == 0 && K3 % 4 == 0 && K4 % 4 == 0 && N % 4 == 0, "rfcr: channels must be multiples of 4");
     YR_CHECK_ARG(op.Ho % 2 == 0 && op.Wo % 2 == 0, "rfcr: output grid must be even");
-    const int nthreads = ((RF_PIX * (N / 4) + 31) / 32) * 32;
-    YR_CHECK_ARG(nthreads <= 1024, "rfcr: N too large");
-    const size_t smem = (size_t)((RF_PIX / 2) * K1 + RF_PIX * K2 + RF_PIX * 4 * K3 + RF_PIX * K4) * sizeof(float);
-    YR_CHECK_ARG(smem <= 48 * 1024, "rfcr: tap channels too large for the staging buffer");
-    dim3 grid(cdiv(op.Wo, RF_PIX), op.Ho, op.B);
-    rfcr_kernel<<<grid, nthreads, smem, s>>>((const float*)op.in, op.ld_in, K1, (const float*)op.in2, op.ld_in2, K2,
-                                             (const float*)op.in3, op.ld_in3, K3, (const float*)op.in4, op.ld_in4, K4,
-                                             op.w, op.bias, (float*)op.out, op.ld_out, op.Ho, op.Wo, N);
+    YR_CHECK_ARG(op.B <= 65535, "rfcr: batch too large");
+    const int W = op.Wo;
+    const size_t smem = ((size_t)(K1 + K2 + K3 + K4) * N + (size_t)(W / 2) * K1 + (size_t)W * K2 + (size_t)W * 4 * K3 +
+                         (size_t)W * K4) * sizeof(float);
+    YR_CHECK_ARG(smem <= 200 * 1024, "rfcr: taps / row too large for shared memory (%zu bytes)", smem);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(rfcr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    dim3 grid(op.Ho, op.B);
+    rfcr_kernel<<<grid, 256, smem, s>>>((const float*)op.in, op.ld_in, K1, (const float*)op.in2, op.ld_in2, K2,
+                                        (const float*)op.in3, op.ld_in3, K3, (const float*)op.in4, op.ld_in4, K4, op.w,
+                                        op.bias, (float*)op.out, op.ld_out, op.Ho, op.Wo, N);
     YR_CHECK_LAUNCH("rfcr");
     return YR_OK;
 }
@@ -438,7 +438,11 @@ se_fc_kernel(const float* __restrict__ part, int slots, int HW, int F, int R, co
         }
     }
     __syncthreads();
-    for (int f = tid; f < F; f += 256) {
+    // second FC: this CTA's slice of the F outputs (gridDim.y CTAs per image share the work; the squeeze
+    // and the first FC above are recomputed per slice - they are tiny, the weight read of FC2 is not)
+    const int per = (F + gridDim.y - 1) / gridDim.y;
+    const int f_end = min(F, (int)(blockIdx.y + 1) * per);
+    for (int f = blockIdx.y * per + tid; f < f_end; f += 256) {
         float a = 0.f;
 #pragma unroll 8
         for (int r = 0; r < R; ++r) a = fmaf(hid[r], __ldg(w2 + (size_t)r * F + f), a);
@@ -453,7 +457,9 @@ int launch_se_fc(const yr_op& op, cudaStream_t s) {
     YR_CHECK_ARG(F % 4 == 0 && R > 0 && slots > 0 && op.H > 0 && op.W > 0, "se_fc: unsupported F=%d R=%d slots=%d", F, R, slots);
     const size_t smem = (size_t)(F + R) * sizeof(float);
     YR_CHECK_ARG(smem <= 48 * 1024, "se_fc: F too large");
-    se_fc_kernel<<<op.B, 256, smem, s>>>((const float*)op.in, slots, op.H * op.W, F, R, op.w, op.bias,
+    YR_CHECK_ARG(op.B <= 65535, "se_fc: batch too large");
+    dim3 grid(op.B, F >= 256 ? 4 : (F >= 128 ? 2 : 1));
+    se_fc_kernel<<<grid, 256, smem, s>>>((const float*)op.in, slots, op.H * op.W, F, R, op.w, op.bias,
                                          op.w + (size_t)F * R, op.bias + R, (float*)op.out);
     YR_CHECK_LAUNCH("se_fc");
     return YR_OK;
