@@ -38,7 +38,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 ANCHORS = [10, 13, 16, 30, 33, 23, 30, 61, 62, 45, 59, 119, 116, 90, 156, 198, 373, 326]
-METRIC = "images/sec at 416x416"
+METRIC = "images/sec at 416x416"  # the headline workload; other --workload values override the size in `config`
 UNIT = "images/s"
 SCORE, IOU = 0.2, 0.5  # YOLO defaults, reference code/yolo.py:176-177
 
@@ -58,7 +58,18 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--ref-images", type=int, default=4, help="images per step of the reference arm")
-    return ap.parse_args()
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5", "post", "post0"],
+                    help="cfg2 = the headline (BASELINE.json configs[1]); cfg3/cfg4 = the other inference configs "
+                         "(per-GPU shard); cfg5 = training-loss step (yolo_loss fwd+bwd + gradient reduce-scatter); "
+                         "post / post0 = yolo_eval alone on synthetic head logits at score 0.2 / 0.0")
+    a = ap.parse_args()
+    if a.workload == "cfg3":    # derived EfficientNet-lite0 320x320, batch 256 over 8 GPUs -> 32 per GPU
+        a.model, a.size, a.batch = "efficientnetlite0", 320, 32
+    elif a.workload == "cfg4":  # MobileNetV2-1.4 608x608, batch 128 over 8 GPUs -> 16 per GPU
+        a.model, a.size, a.batch = "mobilenetv2x14", 608, 16
+    elif a.workload == "cfg5":  # training step, batch 256 over 8 GPUs -> 32 per GPU
+        a.batch = 32
+    return a
 
 
 # ---------------------------------------------------------------------------------------------
@@ -317,7 +328,8 @@ def run_b200(a):
     d2h = eng.pp.d2h_bytes() * (world if (gather is not None) else 1)
 
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "metric": METRIC if a.size == 416 else "images/sec at %dx%d" % (a.size, a.size), "value": value, "unit": UNIT,
+        "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "global_batch": a.batch * world, "micro_batch": eng.micro,
@@ -376,10 +388,107 @@ def run_b200(a):
         print(json.dumps(out))
 
 
+# ---------------------------------------------------------------------------------------------
+def synthetic_head_logits(a, batch, seed):
+    """Head tensors as SURVEY.md section 8d prescribes: t_xy~N(0,1), t_wh~N(0,.5), t_obj~N(-4,2), t_cls~N(-3,2)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    ys = []
+    for s in (32, 16, 8):
+        gh = a.size // s
+        t = torch.randn(batch, gh, gh, 3, a.classes + 5, generator=g)
+        t[..., 2:4] *= 0.5
+        t[..., 4] = t[..., 4] * 2 - 4
+        t[..., 5:] = t[..., 5:] * 2 - 3
+        ys.append(t)
+    return ys
+
+
+def run_aux(a):
+    """Secondary workloads (not the headline line): the training-loss step and the standalone post-process."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from yoloret_b200 import parallel
+    from yoloret_b200.yolo3.model import YoloLoss, yolo_eval
+    from yoloret_b200.yolo3.utils import encode_true_boxes_batch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    anchors = np.array(ANCHORS, np.float32).reshape(-1, 2)
+    hbm, _, which = measured_peaks()
+    ys = [y.to(dev) for y in synthetic_head_logits(a, a.batch, 1234 + rank)]
+    if a.workload == "cfg5":
+        rng = np.random.default_rng(1234 + rank)
+        boxes = []
+        for _ in range(a.batch):  # 8 boxes per image, wh ~ U(0.05, 0.6), SURVEY.md section 8d
+            wh = rng.uniform(0.05, 0.6, (8, 2)) * a.size
+            c = rng.uniform(0.0, 1.0, (8, 2)) * a.size
+            lo, hi = np.clip(c - wh / 2, 0, a.size - 1), np.clip(c + wh / 2, 0, a.size - 1)
+            boxes.append(np.concatenate([lo, hi, rng.integers(0, a.classes, (8, 1))], 1))
+        yts = [torch.from_numpy(t).to(dev) for t in encode_true_boxes_batch(boxes, (a.size, a.size), anchors, a.classes)]
+        losses = [YoloLoss(i, anchors, 3, print_loss=False) for i in range(3)]
+        bucket = parallel.GradBucket(2630000, world, rank, device=dev)  # the 2.63 M-parameter gradient buffer
+        outs = [y.clone().requires_grad_(True) for y in ys]
+
+        def step():
+            total = 0
+            for L, yt, yo in zip(losses, yts, outs):
+                yo.grad = None
+                total = total + L(yt, yo)
+            total.backward()
+            bucket.reduce_scatter()
+            return total
+        what = "yolo_loss fwd+bwd (3 scales, batch %d per GPU) + SUM reduce-scatter of a 2.63M-float gradient bucket" % a.batch
+        alg_bytes = sum(3 * y.numel() * 4 for y in ys)  # read logits + y_true, write dlogits
+    else:
+        thr = 0.2 if a.workload == "post" else 0.0
+
+        def step():
+            return yolo_eval(ys, anchors, 3, a.classes, (a.size, a.size), score_threshold=thr, iou_threshold=IOU,
+                             sync=False)
+        what = "yolo_eval (decode + class-wise NMS + pack) on synthetic head logits, batch %d, score_threshold %.1f" % (
+            a.batch, thr)
+        alg_bytes = sum(y.numel() * 4 for y in ys)
+    for _ in range(max(a.warmup, 3)):
+        step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        per = ms / a.steps
+        print(json.dumps({"metric": "images/sec (%s)" % a.workload, "value": a.batch * world * a.steps / (ms * 1e-3),
+                          "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+                          "ms_per_step": per, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32", "data": "synthetic", "config": {"workload": what},
+                          "roofline": {"bound": "hbm", "achieved": alg_bytes / (per * 1e-3) / 1e9, "peak": hbm,
+                                       "unit": "GB/s", "frac": alg_bytes / (per * 1e-3) / 1e9 / hbm, "traffic": None,
+                                       "peak_source": which, "note": "whole step incl. host launch gaps (eager)"}}))
+
+
 def main():
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload in ("cfg5", "post", "post0"):
+        run_aux(a)
     else:
         run_b200(a)
 

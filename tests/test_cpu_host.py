@@ -149,3 +149,67 @@ def test_detection_all_gather_world2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, True), (1, True)]
+
+
+def _bucket_worker(rank, world, port, numel, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        b = parallel.GradBucket(numel, world, rank)
+        g = torch.arange(numel, dtype=torch.float32) * (rank + 1)   # rank r holds (r+1) * [0..numel)
+        b.view().copy_(g)
+        shard = b.reduce_scatter().clone()
+        lo = rank * b.shard_numel
+        expect = torch.arange(lo, lo + b.shard_numel, dtype=torch.float32) * 3.0   # 1x + 2x
+        expect[max(0, numel - lo):] = 0.0                                          # padding stays zero
+        ok = torch.equal(shard, expect)
+        b.shard.mul_(0.5)                                                          # "optimizer step" on the shard
+        full = b.all_gather()
+        ok = ok and torch.equal(full, torch.arange(numel, dtype=torch.float32) * 1.5)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_grad_bucket_reduce_scatter_world2_gloo():
+    """Training config: flat gradient bucket, SUM reduce-scatter + all-gather, world size 2 on CPU (gloo)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, 1001, q)) for r in range(2)]   # odd size: padding
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
+    b = parallel.GradBucket(10, 1, 0)
+    b.view().fill_(2.0)
+    assert torch.equal(b.reduce_scatter(), torch.full((10,), 2.0)) and torch.equal(b.all_gather(), torch.full((10,), 2.0))
+    with pytest.raises(ValueError):
+        parallel.GradBucket(0, 1, 0)
+
+
+def test_preprocess_true_boxes_matches_oracle():
+    """Host y_true encoder (reference utils.py:298-376) against the oracle's restatement, incl. padding rows."""
+    from yoloret_b200.yolo3.utils import preprocess_true_boxes, encode_true_boxes_batch
+    from oracle import loss as oloss
+    anchors = np.array([10, 13, 16, 30, 33, 23, 30, 61, 62, 45, 59, 119, 116, 90, 156, 198, 373, 326], np.float32).reshape(-1, 2)
+    rng = np.random.default_rng(0)
+    for hw, ncls, n in (((416, 416), 80, 8), ((320, 224), 20, 5), ((96, 96), 4, 0)):
+        wh = rng.uniform(0.02, 0.7, (n, 2)) * np.array(hw[::-1])
+        c = rng.uniform(0.1, 0.9, (n, 2)) * np.array(hw[::-1])
+        lim = np.array([hw[1] - 1, hw[0] - 1])
+        tb = np.concatenate([np.clip(c - wh / 2, 0, lim), np.clip(c + wh / 2, 0, lim), rng.integers(0, ncls, (n, 1))], 1)
+        tb = np.concatenate([tb, np.zeros((3, 5))], 0)  # zero-width padding rows
+        got = preprocess_true_boxes(tb, hw, anchors, ncls)
+        ref = oloss.preprocess_true_boxes(tb, hw, anchors, ncls)
+        assert len(got) == 3
+        for g, r in zip(got, ref):
+            assert g.shape == r.shape and np.array_equal(g, r)
+        assert sum(int(g[..., 4].sum()) for g in got) <= n
+    b = encode_true_boxes_batch([tb, tb], hw, anchors, ncls)
+    assert b[0].shape == (2, 3, 3, 3, 9)

@@ -55,3 +55,47 @@ class DetectionGather:
         if self.wire.is_cuda:
             torch.cuda.current_stream(self.wire.device).synchronize()
         return list(self.host.numpy().reshape(self.world, self.words))
+
+
+class GradBucket:
+    """Data-parallel gradient exchange for the training config (reference: MirroredStrategy's implicit
+    all-reduce, code/train.py:55-56, and the loss SUM of code/yolo3/train.py:66-70).
+
+    All gradients live in ONE flat fp32 bucket (2.63 M elements = 10.5 MB for MobileNetV2-0.75 COCO), padded
+    to a multiple of the world size.  ``reduce_scatter`` leaves each rank with the SUM of its 1/N shard
+    (``ncclReduceScatter`` over NVLink; a sharded optimizer updates that shard), ``all_gather`` rebuilds the
+    full vector (updated parameters).  The reference sums across replicas (it does not average, each
+    replica divides by its LOCAL batch, code/yolo3/model.py:624-625) - so does this."""
+
+    def __init__(self, numel: int, world: int, rank: int, device=None, group=None):
+        if numel <= 0 or world <= 0 or not (0 <= rank < world):
+            raise ValueError("bad bucket: numel=%d world=%d rank=%d" % (numel, world, rank))
+        self.numel, self.world, self.rank, self.group = numel, world, rank, group
+        self.shard_numel = (numel + world - 1) // world
+        self.padded = self.shard_numel * world
+        self.flat = torch.zeros(self.padded, dtype=torch.float32, device=device)
+        self.shard = torch.zeros(self.shard_numel, dtype=torch.float32, device=device)
+
+    def view(self) -> torch.Tensor:
+        """The caller-visible gradient vector (without the padding)."""
+        return self.flat[:self.numel]
+
+    def reduce_scatter(self) -> torch.Tensor:
+        if self.world == 1:
+            self.shard.copy_(self.flat[:self.shard_numel])
+        elif self.flat.is_cuda:
+            dist.reduce_scatter_tensor(self.shard, self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        else:  # gloo has no reduce_scatter: all-reduce then slice (CPU tests only)
+            tmp = self.flat.clone()
+            dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=self.group)
+            self.shard.copy_(tmp[self.rank * self.shard_numel:(self.rank + 1) * self.shard_numel])
+        return self.shard
+
+    def all_gather(self) -> torch.Tensor:
+        if self.world == 1:
+            self.flat[:self.shard_numel].copy_(self.shard)
+        elif self.flat.is_cuda:
+            dist.all_gather_into_tensor(self.flat, self.shard, group=self.group)
+        else:
+            dist.all_gather(list(self.flat.split(self.shard_numel)), self.shard, group=self.group)
+        return self.flat[:self.numel]

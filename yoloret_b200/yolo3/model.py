@@ -144,7 +144,7 @@ def yolo_head(feats: torch.Tensor, anchors, input_shape, calc_loss: bool = False
 
 
 def yolo_eval(yolo_outputs, anchors, num_scales, num_classes, image_shape, max_boxes=20, score_threshold=.6,
-              iou_threshold=.5, zoom_outputs=None):
+              iou_threshold=.5, zoom_outputs=None, sync=True):
     """reference code/yolo3/model.py:431.  Returns (boxes_ int32 [N,4] (ymin,xmin,ymax,xmax),
     scores_ f32 [N], classes_ int32 [N]) as CUDA tensors for a batch of one (as the reference);
     for B > 1 returns per-image lists (batch = independent per-image application)."""
@@ -166,6 +166,8 @@ def yolo_eval(yolo_outputs, anchors, num_scales, num_classes, image_shape, max_b
                                           device=feats[0].device)
     pp.set_image_shapes(image_shape)
     pp.run([t.data_ptr() for t in feats], lds, score_threshold, iou_threshold)
+    if not sync:  # engine extension: leave the packed result on the device (PostProcess buffers), no host read
+        return pp
     cnt = pp.out_count.cpu().numpy()
     if int(pp.status.item()) != 0:
         raise _lib.YrError("candidate list overflow")

@@ -47,3 +47,49 @@ def letterbox_image(image: torch.Tensor, size) -> torch.Tensor:
     _lib.check(_lib.lib().yr_letterbox_u8(image.data_ptr(), ih, iw, out.data_ptr(), h, w, nh, nw, dy, dx, st),
                "yr_letterbox_u8")
     return out
+
+
+_ANCHOR_MASK = [[6, 7, 8], [3, 4, 5], [0, 1, 2]]
+
+
+def preprocess_true_boxes(true_boxes, input_shape, anchors, num_classes, num_scales=3):
+    """y_true encoder, reference code/yolo3/utils.py:298-376 (host-side numpy there too; it runs inside the
+    tf.data pipeline, code/yolo3/data.py:84-121).  ONE image: ``true_boxes`` [T,5] = (xmin, ymin, xmax, ymax,
+    class) in input pixels, rows with zero width are padding.  Returns one array per scale,
+    [gh, gw, 3, 5+num_classes]: (cx, cy, w, h) normalised, objectness, one-hot class - written at the cell
+    holding the box centre, for the anchor (of all 9) whose shape has the best IoU with the box; a later box
+    overwrites an earlier one in the same slot, as the reference's loop does."""
+    mask = _ANCHOR_MASK[-num_scales:]
+    tb = np.array(true_boxes, dtype=np.float32).reshape(-1, 5)
+    hw = np.array(input_shape, dtype=np.int32)
+    wh_in = hw[::-1]
+    centre = (tb[:, 0:2] + tb[:, 2:4]) // 2            # floor-divided centre, utils.py:321
+    size = tb[:, 2:4] - tb[:, 0:2]
+    rel = np.concatenate([centre / wh_in, size / wh_in], 1).astype(np.float32)
+    grids = [np.round(hw / s).astype(np.int32) for s in (32, 16, 8)[:num_scales]]
+    y_true = [np.zeros((g[0], g[1], 3, 5 + num_classes), np.float32) for g in grids]
+    keep = size[:, 0] > 0
+    if not keep.any():
+        return y_true
+    anc = np.asarray(anchors, np.float32).reshape(-1, 2)
+    bw = size[keep]
+    inter = np.minimum(bw[:, None, 0], anc[None, :, 0]) * np.minimum(bw[:, None, 1], anc[None, :, 1])
+    union = bw[:, None, 0] * bw[:, None, 1] + anc[None, :, 0] * anc[None, :, 1] - inter
+    best = np.argmax(inter / union, axis=1)             # centred boxes: IoU of shapes only
+    # the reference enumerates best_anchor (valid boxes only) but indexes true_boxes[t] with that counter
+    # (utils.py:357-368), i.e. valid boxes are assumed to come first; mirrored here
+    for t, n in enumerate(best):
+        for l, m in enumerate(mask):
+            if n in m:
+                i = int(np.floor(rel[t, 0] * grids[l][1]))
+                j = int(np.floor(rel[t, 1] * grids[l][0]))
+                y_true[l][j, i, m.index(n), 0:4] = rel[t]
+                y_true[l][j, i, m.index(n), 4] = 1.0
+                y_true[l][j, i, m.index(n), 5 + int(tb[t, 4])] = 1.0
+    return y_true
+
+
+def encode_true_boxes_batch(boxes_batch, input_shape, anchors, num_classes, num_scales=3):
+    """Stacks ``preprocess_true_boxes`` over a batch: list of [T,5] -> list (per scale) of [B,gh,gw,3,5+C]."""
+    per_image = [preprocess_true_boxes(b, input_shape, anchors, num_classes, num_scales) for b in boxes_batch]
+    return [np.stack([y[l] for y in per_image]) for l in range(num_scales)]
