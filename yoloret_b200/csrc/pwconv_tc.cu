@@ -179,6 +179,14 @@ __device__ __forceinline__ void dbg_mark(const Params& p, int role, uint32_t idx
     if (p.dbg != nullptr && blockIdx.x == 0 && idx < DBG_EV) p.dbg[role * DBG_EV + idx] = clock64();
 }
 
+// Streamed-weight layers walk their tiles in GROUPS of two consecutive M tiles of one n tile: each weight slot
+// is fetched once per group and feeds the k-block of both tiles, which halves the L2 -> SM weight traffic that
+// bounds the wide head layers.  (Resident-weight layers: groups of one.)
+__device__ __forceinline__ int group_size(const Params& p, int item, int item1, int mt) {
+    // needs >= 4 accumulators: with 2 (N > 128) a pair would own all of TMEM and serialise MMA and epilogue
+    return (!p.resident && p.nAcc >= 4 && item + 1 < item1 && mt + 1 < p.m_tiles) ? 2 : 1;
+}
+
 struct Ring {  // (slot, phase) cursor of a circular buffer; no div/mod on the hot path
     uint32_t slot = 0, phase = 0;
     __device__ __forceinline__ void advance(uint32_t n) {
@@ -285,9 +293,12 @@ __device__ __forceinline__ void converter_loop(const Params& p, uint8_t* gbase, 
                                                uint32_t bar0, int item0, int item1, int ct, int grp) {
     Ring ra, rl;
     uint32_t dq = 0;
-    int mt = item0 % p.m_tiles;
-    for (int item = item0; item < item1; ++item) {
-        for (int kb = 0; kb < p.KB; ++kb, ++dq) {
+    int mt0 = item0 % p.m_tiles;
+    for (int item = item0; item < item1;) {
+        const int g = group_size(p, item, item1, mt0);
+        for (int kb = 0; kb < p.KB; ++kb)
+        for (int j = 0; j < g; ++j, ++dq) {
+            const int mt = mt0 + j;
             if ((int)(dq & 1u) == grp) {
                 mbar_wait(bar0 + 8u * (BAR_A_FULL + ra.slot), ra.phase, 5);
                 if (ct == 0) dbg_mark(p, 1, dq);
@@ -330,7 +341,9 @@ __device__ __forceinline__ void converter_loop(const Params& p, uint8_t* gbase, 
             ra.advance(p.nA);
             rl.advance(p.nL);
         }
-        if (++mt == p.m_tiles) mt = 0;
+        item += g;
+        mt0 += g;
+        if (mt0 == p.m_tiles) mt0 = 0;
     }
 }
 
@@ -390,7 +403,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
             bool b_loaded = false;
             uint32_t dq = 0;
             int nt = item0 / p.m_tiles, mt = item0 - nt * p.m_tiles;
-            for (int item = item0; item < item1; ++item) {
+            for (int item = item0; item < item1;) {
+                const int g = group_size(p, item, item1, mt);
                 const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wp) + (size_t)nt * p.KB * b_slot_bytes;
                 for (int kb = 0; kb < p.KB; ++kb) {
                     if (!(p.resident && b_loaded)) {
@@ -400,15 +414,19 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
                                   bar0 + 8u * (BAR_B_FULL + rb.slot));
                         rb.advance(p.nB);
                     }
-                    mbar_wait(bar0 + 8u * (BAR_A_EMPTY + ra.slot), ra.phase ^ 1u, 1);
-                    mbar_expect_tx(bar0 + 8u * (BAR_A_FULL + ra.slot), A_TILE_BYTES);
-                    tma_load_2d(base + a_off + ra.slot * (uint32_t)A_TILE_BYTES, &tmA, bar0 + 8u * (BAR_A_FULL + ra.slot),
-                                kb * BK, mt * BM);
-                    dbg_mark(p, 0, dq++);
-                    ra.advance(p.nA);
+                    for (int j = 0; j < g; ++j) {
+                        mbar_wait(bar0 + 8u * (BAR_A_EMPTY + ra.slot), ra.phase ^ 1u, 1);
+                        mbar_expect_tx(bar0 + 8u * (BAR_A_FULL + ra.slot), A_TILE_BYTES);
+                        tma_load_2d(base + a_off + ra.slot * (uint32_t)A_TILE_BYTES, &tmA,
+                                    bar0 + 8u * (BAR_A_FULL + ra.slot), kb * BK, (mt + j) * BM);
+                        dbg_mark(p, 0, dq++);
+                        ra.advance(p.nA);
+                    }
                 }
                 b_loaded = true;
-                if (++mt == p.m_tiles) { mt = 0; ++nt; }
+                item += g;
+                mt += g;
+                if (mt == p.m_tiles) { mt = 0; ++nt; }
             }
         }
     } else if (warp == 1) {
@@ -419,11 +437,12 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
         // descriptors differ only in the 14-bit start-address field: build one, then add (bytes >> 4)
         const uint64_t desc0 = make_desc_sw128(base);
         const int k_tail = (p.K - (p.KB - 1) * BK + 7) / 8;  // 8-wide K steps of the last k-block
-        for (int item = item0; item < item1; ++item) {
-            const uint32_t acc = racc.slot;
-            mbar_wait(bar0 + 8u * (BAR_ACC_EMPTY + acc), racc.phase ^ 1u, 2);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.acc_stride;
+        int mt = item0 % p.m_tiles;
+        for (int item = item0; item < item1;) {
+            const int g = group_size(p, item, item1, mt);
+            // accumulators of the group's tiles: consecutive slots of the ring
+            Ring racc1 = racc;
+            racc1.advance(p.nAcc);
             for (int kb = 0; kb < p.KB; ++kb) {
                 uint32_t slot;
                 if (p.resident) {
@@ -434,33 +453,44 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
                     mbar_wait(bar0 + 8u * (BAR_B_FULL + slot), rb.phase, 3);
                     rb.advance(p.nB);
                 }
-                mbar_wait(bar0 + 8u * (BAR_A_CONV + ra.slot), ra.phase, 4);
-                tc_fence_after();
-                if (lane == 0) dbg_mark(p, 4, dq);
-                const uint64_t dah = desc0 + ((a_off + ra.slot * (uint32_t)A_TILE_BYTES) >> 4);
-                const uint64_t dal = desc0 + ((l_off + rl.slot * (uint32_t)A_TILE_BYTES) >> 4);
                 const uint64_t dbh = desc0 + ((b_off + slot * b_slot_bytes) >> 4);
                 const uint64_t dbl = dbh + ((p.BN * 128u) >> 4);
                 const int ksteps = (kb == p.KB - 1) ? k_tail : BK / 8;  // skip all-zero K steps of the tail
-                if (elect_one()) {
-                    for (int k8 = 0; k8 < ksteps; ++k8) {
-                        const uint64_t ko = (uint64_t)(k8 * 2);  // 32 bytes per 8-wide TF32 K step
-                        umma_tf32(d_tmem, dal + ko, dbh + ko, p.idesc, (kb | k8) ? 1u : 0u);  // small terms first
-                        umma_tf32(d_tmem, dah + ko, dbl + ko, p.idesc, 1u);
-                        umma_tf32(d_tmem, dah + ko, dbh + ko, p.idesc, 1u);
+                for (int j = 0; j < g; ++j) {
+                    const Ring& rc = j ? racc1 : racc;
+                    if (kb == 0) {  // first MMA into this tile's accumulator: the epilogue must have drained it
+                        mbar_wait(bar0 + 8u * (BAR_ACC_EMPTY + rc.slot), rc.phase ^ 1u, 2);
                     }
-                    umma_commit(bar0 + 8u * (BAR_A_EMPTY + ra.slot));
-                    umma_commit(bar0 + 8u * (BAR_L_EMPTY + rl.slot));
-                    if (!p.resident) umma_commit(bar0 + 8u * (BAR_B_EMPTY + slot));
-                    if (kb == p.KB - 1) umma_commit(bar0 + 8u * (BAR_ACC_FULL + acc));
+                    mbar_wait(bar0 + 8u * (BAR_A_CONV + ra.slot), ra.phase, 4);
+                    tc_fence_after();
+                    if (lane == 0) dbg_mark(p, 4, dq);
+                    const uint32_t d_tmem = tmem_base + rc.slot * (uint32_t)p.acc_stride;
+                    const uint64_t dah = desc0 + ((a_off + ra.slot * (uint32_t)A_TILE_BYTES) >> 4);
+                    const uint64_t dal = desc0 + ((l_off + rl.slot * (uint32_t)A_TILE_BYTES) >> 4);
+                    if (elect_one()) {
+                        for (int k8 = 0; k8 < ksteps; ++k8) {
+                            const uint64_t ko = (uint64_t)(k8 * 2);  // 32 bytes per 8-wide TF32 K step
+                            umma_tf32(d_tmem, dal + ko, dbh + ko, p.idesc, (kb | k8) ? 1u : 0u);  // small terms first
+                            umma_tf32(d_tmem, dah + ko, dbl + ko, p.idesc, 1u);
+                            umma_tf32(d_tmem, dah + ko, dbh + ko, p.idesc, 1u);
+                        }
+                        umma_commit(bar0 + 8u * (BAR_A_EMPTY + ra.slot));
+                        umma_commit(bar0 + 8u * (BAR_L_EMPTY + rl.slot));
+                        if (!p.resident && j == g - 1) umma_commit(bar0 + 8u * (BAR_B_EMPTY + slot));
+                        if (kb == p.KB - 1) umma_commit(bar0 + 8u * (BAR_ACC_FULL + rc.slot));
+                    }
+                    __syncwarp();
+                    if (lane == 0) dbg_mark(p, 5, dq);
+                    ++dq;
+                    ra.advance(p.nA);
+                    rl.advance(p.nL);
                 }
-                __syncwarp();
-                if (lane == 0) dbg_mark(p, 5, dq);
-                ++dq;
-                ra.advance(p.nA);
-                rl.advance(p.nL);
             }
             racc.advance(p.nAcc);
+            if (g == 2) racc.advance(p.nAcc);
+            item += g;
+            mt += g;
+            if (mt == p.m_tiles) mt = 0;
         }
     } else if (warp < 2 + NUM_CONVERTERS / 32) {
         const int ct = (threadIdx.x - 64) & 127, cg = (threadIdx.x - 64) >> 7;  // thread within group, group
