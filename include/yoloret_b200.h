@@ -47,7 +47,8 @@ typedef enum yr_op_kind {
     YR_OP_RESAMPLE = 3,  /* nearest x2 up-sampling / 2x2 / 4x4 max-pooling into a channel slice */
     YR_OP_RFCR = 4,      /* fused RFCR fusion: 4x 1x1 conv + resize + weighted sum */
     YR_OP_SE = 5,        /* squeeze-excite gate: global mean -> FC -> swish -> FC -> sigmoid */
-    YR_OP_SE_FC = 6      /* the same gate from the channel sums a DW op left in `aux` (fused squeeze) */
+    YR_OP_SE_FC = 6,     /* the same gate from the channel sums a DW op left in `aux` (fused squeeze) */
+    YR_OP_MBCONV = 7     /* fused inverted-residual block: 1x1 expand + 3x3 depthwise + 1x1 project (+ residual) */
 } yr_op_kind;
 
 typedef enum yr_resample_mode { YR_UP2 = 0, YR_POOL2 = 1, YR_POOL4 = 2 } yr_resample_mode;
@@ -87,6 +88,11 @@ typedef enum yr_resample_mode { YR_UP2 = 0, YR_POOL2 = 1, YR_POOL4 = 2 } yr_resa
  *  SE_FC    in = the aux buffer of the producing DW op [B][K2 slots][C=F]; H,W = spatial size of the
  *           squeezed tensor; w = [w1^T R x F | w2 R x F] (first FC TRANSPOSED), bias = b1[R] then b2[F];
  *           N = R; out = gate [B][F].
+ *  MBCONV   in [B,H,W,ld_in] C=Cin (<= 32); K2 = expanded channels Ce (<= 160); N = Cout (<= 32);
+ *           k=3, stride 1|2, pad_t/pad_l = leading TF-SAME pads of the depthwise; ReLU6 after expand and
+ *           depthwise, linear project; res optional [B,Ho,Wo,ld_res] (stride 1); w_tc = yr_mbconv_pack image
+ *           of the three layers' folded weights; out [B,Ho,Wo,ld_out].  One kernel for block_N_expand ..
+ *           block_N_add of tf.keras.applications.MobileNetV2 (reference code/yolo3/override.py:339-341).
  *  SE       in [B,H,W,ld_in] C=F channels; w = [F][R] then [R][F] (w2 = w + F*R),
  *           bias = b1[R] then b2[F]; N = R; out = gate [B][F].
  *           SEBlock, efficientnet.py:406-438.
@@ -135,6 +141,14 @@ int yr_run_ops(const yr_op* ops, int n_ops, void* stream);
  *   yr_pw_tc_pack           packed must be 128-byte aligned */
 int64_t yr_pw_tc_packed_floats(int K, int N);
 int yr_pw_tc_pack(const float* w, int K, int N, float* packed, void* stream);
+
+/* Fused inverted-residual block (YR_OP_MBCONV): packs the folded weights of its three layers -
+ *   w1 [Cin][ld1] + b1[Ce] (expand), wd [9][ldd] + b2[Ce] (depthwise), w2 [Ce][ld2] + b3[Cout] (project) -
+ * into the shared-memory image the kernel bulk-copies.  yr_mbconv_packed_floats returns 0 when the block
+ * does not fit the fused kernel (the caller then runs the three ops separately). */
+int64_t yr_mbconv_packed_floats(int Cin, int Ce, int Cout);
+int yr_mbconv_pack(const float* w1, int ld1, const float* b1, const float* wd, int ldd, const float* b2,
+                   const float* w2, int ld2, const float* b3, int Cin, int Ce, int Cout, float* packed, void* stream);
 
 /* ---- post-process: yolo_eval (reference code/yolo3/model.py:431-491) --------- */
 

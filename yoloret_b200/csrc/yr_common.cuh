@@ -58,6 +58,7 @@ int launch_resample(const yr_op& op, cudaStream_t s);
 int launch_rfcr(const yr_op& op, cudaStream_t s);
 int launch_se(const yr_op& op, cudaStream_t s);
 int launch_se_fc(const yr_op& op, cudaStream_t s);
+int launch_mbconv(const yr_op& op, cudaStream_t s);
 int dw_se_slots(const yr_op& op);
 
 }  // namespace yr

@@ -61,7 +61,7 @@ class Engine:
                  weights: Dict[str, np.ndarray], anchors: np.ndarray, micro_batch: Optional[int] = None,
                  num_scales: int = 3, max_boxes: int = 20, cand_cap: Optional[int] = None,
                  device: Optional[torch.device] = None, pw_variant: int = _lib.PW_AUTO, input_u8: bool = False,
-                 fuse_se: bool = True):
+                 fuse_se: bool = True, fuse_mbconv: bool = True):
         if not torch.cuda.is_available():
             raise _lib.YrError("yoloret_b200.Engine needs a CUDA device (no CPU fallback exists)")
         self.lib = _lib.lib()
@@ -75,6 +75,7 @@ class Engine:
         self.input_u8 = input_u8
         self.pw_variant = pw_variant
         self.fuse_se = fuse_se
+        self.fuse_mbconv = fuse_mbconv
         self.cand_cap_arg = cand_cap
         self._check_weights(weights)
         self._alloc()
@@ -164,8 +165,44 @@ class Engine:
                         for cn, v in zip(L.extra["convs"], L.inp)]
                 mat = _pad_cols(np.concatenate(mats, 0), L.out.C)
                 self.wdev[i] = (self._dev(mat), self._dev(w["weighted_sum/alpha"]))
+        self._find_fused_blocks()
         torch.cuda.synchronize(self.device)
         self.weight_bytes = sum(a.numel() * 4 + b.numel() * 4 for a, b in self.wdev.values())
+
+    def _find_fused_blocks(self):
+        """Inverted-residual blocks (1x1 expand+ReLU6 -> 3x3 depthwise+ReLU6 -> linear 1x1 project [+ add]) whose
+        channels fit the fused kernel run as ONE yr_op (YR_OP_MBCONV); their weight blobs are packed here."""
+        self.mb_blob: Dict[int, torch.Tensor] = {}
+        if not self.fuse_mbconv or self.pw_variant == _lib.PW_SIMT:
+            return
+        Ls = self.net.layers
+        consumers: Dict[str, int] = {}
+        for L in Ls:
+            for v in L.inp + ([L.res] if L.res is not None else []):
+                consumers[v.buf.name] = consumers.get(v.buf.name, 0) + 1
+        for i in range(len(Ls) - 2):
+            a, d, b = Ls[i], Ls[i + 1], Ls[i + 2]
+            ok = (a.kind == "pw" and a.act == "relu6" and a.res is None and a.gate is None
+                  and d.kind == "dw" and d.k == 3 and d.act == "relu6" and d.inp[0].buf is a.out.buf and d.inp[0].off == a.out.off
+                  and b.kind == "pw" and b.act == "none" and b.gate is None and b.inp[0].buf is d.out.buf
+                  and b.inp[0].off == d.out.off and not self.se_fused.get(i + 2)
+                  and consumers.get(a.out.buf.name, 0) == 1 and consumers.get(d.out.buf.name, 0) == 1
+                  and a.out.buf.ld == a.out.C and d.out.buf.ld == d.out.C)
+            if not ok:
+                continue
+            cin, ce, cout = a.inp[0].C, a.out.C, b.out.C
+            n = int(self.lib.yr_mbconv_packed_floats(cin, ce, cout))
+            if n <= 0:
+                continue
+            blob = torch.zeros(n, dtype=torch.float32, device=self.device)
+            w1, b1 = self.wdev[i]
+            wd, b2 = self.wdev[i + 1]
+            w2, b3 = self.wdev[i + 2]
+            _lib.check(self.lib.yr_mbconv_pack(w1.data_ptr(), int(w1.shape[1]), b1.data_ptr(), wd.data_ptr(),
+                                               int(wd.shape[1]), b2.data_ptr(), w2.data_ptr(), int(w2.shape[1]),
+                                               b3.data_ptr(), cin, ce, cout, blob.data_ptr(), self._stream()),
+                       "yr_mbconv_pack")
+            self.mb_blob[i] = blob
 
     def _pack_tc(self, w_kn: torch.Tensor) -> Optional[torch.Tensor]:
         """yr_pw_tc_pack: [K,N] fp32 -> split/swizzled TF32 (hi, lo) image for the tcgen05 kernel."""
@@ -200,9 +237,36 @@ class Engine:
             return self._plans[key]
         ops = (YrOp * len(self.net.layers))()
         gate_ptr: Dict[int, int] = {}
+        meta = []   # per emitted op: (kind, name, algorithmic bytes / image, flops / image, layer index)
+        n_ops = 0
+        skip = 0
         for i, L in enumerate(self.net.layers):
-            o = ops[i]
+            if skip:
+                skip -= 1
+                continue
+            o = ops[n_ops]
+            n_ops += 1
             x = L.inp[0]
+            if i in self.mb_blob:
+                d, b = self.net.layers[i + 1], self.net.layers[i + 2]
+                o.kind = _lib.OP_MBCONV
+                o.B, o.H, o.W, o.C = nb, x.H, x.W, x.C
+                o.K2 = L.out.C
+                o.Ho, o.Wo, o.N = b.out.H, b.out.W, b.out.C
+                o.k, o.stride = 3, d.stride
+                o.pad_t, o.pad_l = d.extra.get("pad_t", 0), d.extra.get("pad_l", 0)
+                o.ld_in, o.ld_out = x.buf.ld, b.out.buf.ld
+                o.in_ = self._ptr(x, chunk0, slot)
+                o.out = self._ptr(b.out, chunk0)
+                o.w_tc = self.mb_blob[i].data_ptr()
+                if b.res is not None:
+                    o.res, o.ld_res = self._ptr(b.res, chunk0), b.res.buf.ld
+                fused_bytes = 4 * (x.H * x.W * x.Clog + b.out.H * b.out.W * b.out.Clog * (2 if b.res is not None else 1)) \
+                    + self.mb_blob[i].numel() * 4
+                meta.append(("mbconv", L.name.replace("_expand", "") + "_fused", fused_bytes, L.flops + d.flops + b.flops, i))
+                skip = 2
+                continue
+            meta.append((L.kind, L.name, L.bytes_alg, L.flops, i))
             o.act = _ACT[L.act]
             o.B, o.H, o.W, o.C = nb, x.H, x.W, x.C
             o.Ho, o.Wo, o.N = L.out.H, L.out.W, L.out.C
@@ -254,7 +318,8 @@ class Engine:
                 o.in_, o.in2, o.in3, o.in4 = (self._ptr(v, chunk0) for v in (b1, b2, b3, b4))
             else:
                 raise ValueError(L.kind)
-        self._plans[key] = (ops, len(self.net.layers))
+        self._plans[key] = (ops, n_ops)
+        self._plan_meta = meta
         return self._plans[key]
 
     # ---- execution ------------------------------------------------------------------
@@ -318,8 +383,9 @@ class Engine:
         "launches"}`` for one step over the whole batch."""
         st = self._stream()
         net = self.net
-        n_layers = len(net.layers)
         chunks = [(c0, min(self.micro, self.batch - c0)) for c0 in range(0, self.batch, self.micro)]
+        n_layers = self.build_plan(chunks[0][0], chunks[0][1])[1]
+        meta = list(self._plan_meta)
         acc = np.zeros(n_layers + 3)
         for _ in range(reps):
             evs = []
@@ -344,9 +410,9 @@ class Engine:
                 acc[n_layers + j] += pp_ev[j].elapsed_time(pp_ev[j + 1])
         acc /= reps
         out = []
-        for i, L in enumerate(net.layers):
-            out.append(dict(kind=L.kind, name=L.name, ms=float(acc[i]), bytes=int(L.bytes_alg) * self.batch,
-                            flops=int(L.flops) * self.batch, launches=len(chunks)))
+        for i, (kind, name, byts, flops, _li) in enumerate(meta):
+            out.append(dict(kind=kind, name=name, ms=float(acc[i]), bytes=int(byts) * self.batch,
+                            flops=int(flops) * self.batch, launches=len(chunks)))
         E = self.num_classes + 5
         dec_bytes = self.batch * self.total_boxes * (E + 4) * 4
         out.append(dict(kind="decode", name="decode_filter", ms=float(acc[n_layers]), bytes=dec_bytes, flops=0, launches=1))
