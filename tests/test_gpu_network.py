@@ -69,7 +69,7 @@ def test_fused_blocks_equal_unfused(built_lib, anchors):
     nd = NetDef("mobilenetv2x75", ncls, hw)
     w = synthetic_weights(nd.weight_shapes, ncls, seed=21)
     x = torch.rand(B, hw[0], hw[1], 3, generator=torch.Generator().manual_seed(5)).cuda()
-    mf = yolov3_body((B, hw[0], hw[1], 3), "mobilenetv2x75", 3, num_classes=ncls).set_weights(w, anchors)
+    mf = yolov3_body((B, hw[0], hw[1], 3), "mobilenetv2x75", 3, num_classes=ncls, fuse_mbconv=True).set_weights(w, anchors)
     mu = yolov3_body((B, hw[0], hw[1], 3), "mobilenetv2x75", 3, num_classes=ncls, fuse_mbconv=False).set_weights(w, anchors)
     assert len(mf.engine.mb_blob) >= 4 and len(mu.engine.mb_blob) == 0
     yf = [y.clone() for y in mf(x)]

@@ -47,7 +47,13 @@ struct Params {
     int tiles_x, tiles_y, total_tiles, tiles_per_cta, ks1;
     uint32_t idesc1, idesc2;
     uint32_t off_w1, off_w2, off_wd, off_b1, off_b2, off_b3, blob_bytes;  // byte offsets inside the blob
+    long long* dbg;  // optional timeline of CTA 0 (YR_MBCONV_DEBUG=1), else NULL
 };
+
+constexpr int DBG_EV = 64;
+__device__ __forceinline__ void dbg_mark(const Params& p, int role, uint32_t idx) {
+    if (p.dbg != nullptr && blockIdx.x == 0 && idx < DBG_EV) p.dbg[role * DBG_EV + idx] = clock64();
+}
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
     asm volatile(
@@ -57,6 +63,112 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 }
 
 __device__ __forceinline__ float relu6f(float v) { return fminf(fmaxf(v, 0.0f), 6.0f); }
+
+
+// ---- depthwise phase: E (fp32, swizzled rows of 32 channels) -> P (TF32 hi/lo A tile) ----------------
+// Thread = (channel quad c4, output column ox, vertical strip): a strip of VS outputs reuses the loaded input
+// rows from registers (s=1: 4 outputs from 6x3 taps).  Compile-time stride / tile sizes keep address math cheap.
+template <int S>
+__device__ __forceinline__ void dw_phase(const uint8_t* __restrict__ e_s, uint8_t* __restrict__ ph_s, uint8_t* __restrict__ pl_s,
+                                         const float* __restrict__ wd_s, const float* __restrict__ b2_s, int CeP, int cc, int Ce,
+                                         int tid) {
+    constexpr int TOW = 16;
+    constexpr int IW = (TOW - 1) * S + 3;
+    constexpr int VS = S == 1 ? 4 : 2;           // outputs per thread (vertical strip); s=1: 8 rows = 2 strips, s=2: 2 rows = 1 strip
+    constexpr int IN_ROWS = (VS - 1) * S + 3;
+    const int c4 = tid & 7, ox = (tid >> 3) & 15, strip = tid >> 7;
+    const int c = cc * 32 + c4 * 4;
+    if (c >= Ce || (S == 2 && strip > 0)) return;
+    float4 wv[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wv[k] = *reinterpret_cast<const float4*>(wd_s + k * CeP + c);
+    const float4 bv = *reinterpret_cast<const float4*>(b2_s + c);
+    float4 acc[VS];
+#pragma unroll
+    for (int r = 0; r < VS; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int oy_base = strip * VS;
+#pragma unroll
+    for (int ir = 0; ir < IN_ROWS; ++ir) {
+        const int hp0 = (oy_base * S + ir) * IW + ox * S;
+        float4 x[3];
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+            const int hp = hp0 + kw;
+            x[kw] = *reinterpret_cast<const float4*>(e_s + hp * 128 + ((c4 ^ (hp & 7)) << 4));
+        }
+#pragma unroll
+        for (int r = 0; r < VS; ++r) {
+            const int kh = ir - r * S;
+            if (kh < 0 || kh > 2) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const float4 ww = wv[kh * 3 + kw];
+                acc[r].x = fmaf(x[kw].x, ww.x, acc[r].x);
+                acc[r].y = fmaf(x[kw].y, ww.y, acc[r].y);
+                acc[r].z = fmaf(x[kw].z, ww.z, acc[r].z);
+                acc[r].w = fmaf(x[kw].w, ww.w, acc[r].w);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < VS; ++r) {
+        const int op = (oy_base + r) * TOW + ox;
+        float4 o, h, l;
+        o.x = relu6f(acc[r].x + bv.x); o.y = relu6f(acc[r].y + bv.y);
+        o.z = relu6f(acc[r].z + bv.z); o.w = relu6f(acc[r].w + bv.w);
+        h.x = tf32_rna(o.x); h.y = tf32_rna(o.y); h.z = tf32_rna(o.z); h.w = tf32_rna(o.w);
+        l.x = tf32_rna(o.x - h.x); l.y = tf32_rna(o.y - h.y); l.z = tf32_rna(o.z - h.z); l.w = tf32_rna(o.w - h.w);
+        const uint32_t off = op * 128 + ((c4 ^ (op & 7)) << 4);
+        *reinterpret_cast<float4*>(ph_s + off) = h;
+        *reinterpret_cast<float4*>(pl_s + off) = l;
+    }
+}
+
+// ---- final epilogue of a tile: D (TMEM) + bias (+ residual) -> out.  All 8 worker warps: the two warps that
+// share a TMEM lane quarter take 16 of the (<= 32) output channels each.
+struct TileGeo {
+    int b, oy0, ox0;
+};
+
+__device__ __forceinline__ void epilogue2(const Params& p, const TileGeo& tg, uint32_t tmem_base, uint32_t db, const float* b3_s,
+                                          int warp, int w, int lane) {
+    const int q4 = warp & 3, half = w >> 2;  // lane quarter, channel half (0: channels 0..15, 1: 16..31)
+    const int op = q4 * 32 + lane;
+    const int oy = op / p.TOW, ox = op - oy * p.TOW;
+    const int gy = tg.oy0 + oy, gx = tg.ox0 + ox;
+    const bool ok = op < p.n_px && gy < p.Ho && gx < p.Wo && half * 16 < p.Cout;
+    const size_t pix = ((size_t)tg.b * p.Ho + gy) * p.Wo + gx;
+    float4 rv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok && p.res != nullptr) {  // residual first: its latency overlaps the TMEM load
+        const float* r = p.res + pix * p.ld_res + half * 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (half * 16 + j * 4 < p.Cout) rv[j] = ldg4(r + j * 4);
+    }
+    uint32_t u[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+          "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+        : "r"(tmem_base + ((uint32_t)(q4 * 32) << 16) + D_COL0 + db * 32u + (uint32_t)half * 16u)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (ok) {
+        float* o = p.out + pix * p.ld_out + half * 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (half * 16 + j * 4 < p.Cout) {
+                const float4 bv = *reinterpret_cast<const float4*>(b3_s + half * 16 + j * 4);
+                float4 x = make_float4(__uint_as_float(u[4 * j]) + bv.x, __uint_as_float(u[4 * j + 1]) + bv.y,
+                                       __uint_as_float(u[4 * j + 2]) + bv.z, __uint_as_float(u[4 * j + 3]) + bv.w);
+                x.x += rv[j].x; x.y += rv[j].y; x.z += rv[j].z; x.w += rv[j].w;
+                st4(o + j * 4, x);
+            }
+        }
+    }
+}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const Params p) {
@@ -195,6 +307,7 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const Params p) {
         uint8_t* pl_s = g + o_pl;
         mbar_wait(bar(W_FULL), 0, 16);
         uint32_t t = 0, q = 0;
+        TileGeo prev{0, 0, 0};
         for (int tile = tile0; tile < tile1; ++tile, ++t) {
             const int b = tile / tiles_img, rr = tile - b * tiles_img;
             const int ty = rr / p.tiles_x, tx = rr - ty * p.tiles_x;
@@ -203,6 +316,7 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const Params p) {
             // ---- halo -> TF32 (hi, lo)
             mbar_wait(bar(X_FULL), t & 1u, 17);
             mbar_wait(bar(XHL_FREE), (t & 1u) ^ 1u, 18);
+            if (tid == 0) dbg_mark(p, 0, t);
             for (int i = tid; i < p.HR * 8; i += NUM_WORKERS) {
                 const float4 v = xraw[i];
                 float4 h, l;
@@ -214,6 +328,16 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const Params p) {
             fence_proxy_async();
             mbar_arrive(bar(XC_READY));
             mbar_arrive(bar(X_FREE));
+            if (tid == 0) dbg_mark(p, 1, t);
+            if (t > 0) {  // previous tile: D + bias (+ residual) -> out, while the MMA warp starts this tile's expand
+                const uint32_t tp = t - 1;
+                mbar_wait(bar(D_FULL0 + (tp & 1u)), (tp >> 1) & 1u, 21);
+                tc_fence_after();
+                if (tid == 0) dbg_mark(p, 7, tp);
+                epilogue2(p, prev, tmem_base, tp & 1u, b3_s, warp, w, lane);
+                tc_fence_before();
+                mbar_arrive(bar(D_FREE0 + (tp & 1u)));
+            }
             // this thread's expanded-tile row (epilogue 1): is its pixel inside the image?
             const int e_mt = w >> 2, e_q = warp & 3;  // TMEM lane quarter = CTA warp index % 4
             const int hp_e = e_mt * 128 + e_q * 32 + lane;
@@ -228,6 +352,7 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const Params p) {
                 // ---- expand accumulator -> +bias, ReLU6, zero outside the image -> E (128 B per halo pixel, swizzled)
                 mbar_wait(bar(E_FULL0 + eb), u & 1u, 19);
                 tc_fence_after();
+                if (tid == 0) dbg_mark(p, 2, q);
                 {
                     float v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(e_q * 32) << 16) + eb * 64u + (uint32_t)e_mt * 32u, v);
@@ -248,79 +373,27 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const Params p) {
                 tc_fence_before();
                 mbar_arrive(bar(E_FREE0 + eb));
                 asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (tid == 0) dbg_mark(p, 3, q);
                 // ---- depthwise 3x3 over E -> +bias, ReLU6 -> TF32 (hi, lo) A tile of the project GEMM
                 mbar_wait(bar(P_FREE), (q & 1u) ^ 1u, 20);
-                {
-                    const int c4 = tid & 7;
-                    const int c = cc * 32 + c4 * 4;
-                    if (c < p.Ce) {
-                        float4 wv[9];
-#pragma unroll
-                        for (int k = 0; k < 9; ++k) wv[k] = *reinterpret_cast<const float4*>(wd_s + k * CeP + c);
-                        const float4 bv = *reinterpret_cast<const float4*>(b2_s + c);
-                        for (int op = tid >> 3; op < p.n_px; op += NUM_WORKERS / 8) {
-                            const int oy = op / p.TOW, ox = op - oy * p.TOW;
-                            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                            for (int kh = 0; kh < 3; ++kh) {
-#pragma unroll
-                                for (int kw = 0; kw < 3; ++kw) {
-                                    const int hp = (oy * p.stride + kh) * p.IW + ox * p.stride + kw;
-                                    const float4 x = *reinterpret_cast<const float4*>(e_s + hp * 128 + ((c4 ^ (hp & 7)) << 4));
-                                    const float4 ww = wv[kh * 3 + kw];
-                                    acc.x = fmaf(x.x, ww.x, acc.x);
-                                    acc.y = fmaf(x.y, ww.y, acc.y);
-                                    acc.z = fmaf(x.z, ww.z, acc.z);
-                                    acc.w = fmaf(x.w, ww.w, acc.w);
-                                }
-                            }
-                            float4 o, h, l;
-                            o.x = relu6f(acc.x + bv.x); o.y = relu6f(acc.y + bv.y);
-                            o.z = relu6f(acc.z + bv.z); o.w = relu6f(acc.w + bv.w);
-                            h.x = tf32_rna(o.x); h.y = tf32_rna(o.y); h.z = tf32_rna(o.z); h.w = tf32_rna(o.w);
-                            l.x = tf32_rna(o.x - h.x); l.y = tf32_rna(o.y - h.y);
-                            l.z = tf32_rna(o.z - h.z); l.w = tf32_rna(o.w - h.w);
-                            const uint32_t off = op * 128 + ((c4 ^ (op & 7)) << 4);
-                            *reinterpret_cast<float4*>(ph_s + off) = h;
-                            *reinterpret_cast<float4*>(pl_s + off) = l;
-                        }
-                    }
-                }
+                if (tid == 0) dbg_mark(p, 4, q);
+                if (p.stride == 1) dw_phase<1>(e_s, ph_s, pl_s, wd_s, b2_s, CeP, cc, p.Ce, tid);
+                else dw_phase<2>(e_s, ph_s, pl_s, wd_s, b2_s, CeP, cc, p.Ce, tid);
+                if (tid == 0) dbg_mark(p, 5, q);
                 fence_proxy_async();
                 mbar_arrive(bar(P_READY));
                 asm volatile("bar.sync 1, 256;" ::: "memory");  // E may be overwritten by the next chunk now
+                if (tid == 0) dbg_mark(p, 6, q);
             }
-            // ---- project accumulator -> +bias (+ residual) -> out
-            const uint32_t db = t & 1u, vph = t >> 1;
-            mbar_wait(bar(D_FULL0 + db), vph & 1u, 21);
+            prev = TileGeo{b, oy0, ox0};  // its final epilogue runs after the NEXT tile's halo conversion
+        }
+        if (t > 0) {  // final epilogue of the last tile
+            const uint32_t tp = t - 1;
+            mbar_wait(bar(D_FULL0 + (tp & 1u)), (tp >> 1) & 1u, 21);
             tc_fence_after();
-            if (w < 4) {
-                float v[32];
-                const int dq4 = warp & 3;  // TMEM lane quarter = CTA warp index % 4 (warps 2..5 cover all four)
-                tmem_ld32(tmem_base + ((uint32_t)(dq4 * 32) << 16) + D_COL0 + db * 32u, v);
-                const int op = dq4 * 32 + lane;
-                const int oy = op / p.TOW, ox = op - oy * p.TOW;
-                const int gy = oy0 + oy, gx = ox0 + ox;
-                if (op < p.n_px && gy < p.Ho && gx < p.Wo) {
-                    const size_t pix = ((size_t)b * p.Ho + gy) * p.Wo + gx;
-                    float* o = p.out + pix * p.ld_out;
-                    const float* r = p.res ? p.res + pix * p.ld_res : nullptr;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (j * 4 < p.Cout) {
-                            const float4 bv = *reinterpret_cast<const float4*>(b3_s + j * 4);
-                            float4 x = make_float4(v[4 * j] + bv.x, v[4 * j + 1] + bv.y, v[4 * j + 2] + bv.z, v[4 * j + 3] + bv.w);
-                            if (r) {
-                                const float4 rv = ldg4(r + j * 4);
-                                x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w;
-                            }
-                            st4(o + j * 4, x);
-                        }
-                    }
-                }
-            }
+            epilogue2(p, prev, tmem_base, tp & 1u, b3_s, warp, w, lane);
             tc_fence_before();
-            mbar_arrive(bar(D_FREE0 + db));
+            mbar_arrive(bar(D_FREE0 + (tp & 1u)));
         }
     }
 
@@ -467,8 +540,31 @@ int launch_mbconv(const yr_op& op, cudaStream_t s) {
         }
         attr_set = true;
     }
+    p.dbg = nullptr;
+    static const bool debug = getenv("YR_MBCONV_DEBUG") != nullptr;  // developer aid only: timeline of CTA 0
+    if (debug) {
+        static long long* dbuf = nullptr;
+        if (!dbuf) cudaMalloc(&dbuf, 8 * DBG_EV * sizeof(long long));
+        cudaMemsetAsync(dbuf, 0, 8 * DBG_EV * sizeof(long long), s);
+        p.dbg = dbuf;
+    }
     mbconv_kernel<<<grid, NUM_THREADS, smem_bytes(bl), s>>>(tm, p);
     YR_CHECK_LAUNCH("mbconv");
+    if (debug) {
+        static long long h[8 * DBG_EV];
+        cudaStreamSynchronize(s);
+        cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        const char* names[8] = {"x_ready(t)", "conv_done(t)", "e_full(q)", "epi1_done(q)", "p_free(q)", "dw_done(q)",
+                                "chunk_end(q)", "d_full(t)"};
+        const long long t0 = h[0];
+        fprintf(stderr, "mbconv timeline Cin=%d Ce=%d Cout=%d s=%d NC=%d tiles/cta=%d (cycles since first x_ready)\n", Cin, Ce,
+                Cout, op.stride, p.NC, p.tiles_per_cta);
+        for (int r = 0; r < 8; ++r) {
+            fprintf(stderr, "%-14s", names[r]);
+            for (int i = 0; i < 22 && h[r * DBG_EV + i]; ++i) fprintf(stderr, " %6lld", h[r * DBG_EV + i] - t0);
+            fprintf(stderr, "\n");
+        }
+    }
     return YR_OK;
 }
 

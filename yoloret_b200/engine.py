@@ -61,7 +61,7 @@ class Engine:
                  weights: Dict[str, np.ndarray], anchors: np.ndarray, micro_batch: Optional[int] = None,
                  num_scales: int = 3, max_boxes: int = 20, cand_cap: Optional[int] = None,
                  device: Optional[torch.device] = None, pw_variant: int = _lib.PW_AUTO, input_u8: bool = False,
-                 fuse_se: bool = True, fuse_mbconv: bool = True):
+                 fuse_se: bool = True, fuse_mbconv: bool = False):
         if not torch.cuda.is_available():
             raise _lib.YrError("yoloret_b200.Engine needs a CUDA device (no CPU fallback exists)")
         self.lib = _lib.lib()
@@ -171,7 +171,10 @@ class Engine:
 
     def _find_fused_blocks(self):
         """Inverted-residual blocks (1x1 expand+ReLU6 -> 3x3 depthwise+ReLU6 -> linear 1x1 project [+ add]) whose
-        channels fit the fused kernel run as ONE yr_op (YR_OP_MBCONV); their weight blobs are packed here."""
+        channels fit the fused kernel run as ONE yr_op (YR_OP_MBCONV); their weight blobs are packed here.
+        Opt-in (``fuse_mbconv=True``): bit-identical to the three separate ops, but measured SLOWER at batch 64 on
+        B200 (the fused kernel is shared-memory-bandwidth bound, the separate ops stream HBM at 3.6-6 TB/s;
+        DESIGN.md section 4)."""
         self.mb_blob: Dict[int, torch.Tensor] = {}
         if not self.fuse_mbconv or self.pw_variant == _lib.PW_SIMT:
             return

@@ -34,7 +34,7 @@ class YoloBody:
     ``load_weights`` / ``set_weights`` (reference: an ``AdvLossModel``, model.py:342)."""
 
     def __init__(self, input_shape, model_name, num_anchors, num_classes, micro_batch=None, device=None,
-                 pw_variant=_lib.PW_AUTO, input_u8=False, num_scales=3, fuse_se=True, fuse_mbconv=True):
+                 pw_variant=_lib.PW_AUTO, input_u8=False, num_scales=3, fuse_se=True, fuse_mbconv=False):
         self.batch, self.input_hw = int(input_shape[0]), (int(input_shape[1]), int(input_shape[2]))
         self.model_name, self.num_anchors, self.num_classes = model_name, num_anchors, num_classes
         self._kw = dict(micro_batch=micro_batch, device=device, pw_variant=pw_variant, input_u8=input_u8,
