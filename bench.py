@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
     ap.add_argument("--micro", type=int, default=0, help="micro-batch (0 = engine default)")
     ap.add_argument("--pw-variant", type=int, default=0)
+    ap.add_argument("--lanes", type=int, default=1, help="concurrent micro-batch lanes (streams) inside a step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--ref-images", type=int, default=4, help="images per step of the reference arm")
@@ -245,6 +246,7 @@ def run_b200(a):
              "nms": IOU, "weights": weights, "batch": a.batch, "pw_variant": a.pw_variant, "quiet": True}
     if a.micro:
         flags["micro_batch"] = a.micro
+    flags["lanes"] = a.lanes
     yolo = YOLO(flags)
     eng = yolo.engine
     gather = parallel.DetectionGather(eng.pp, world, rank) if world > 1 else None
@@ -332,7 +334,7 @@ def run_b200(a):
         "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "global_batch": a.batch * world, "micro_batch": eng.micro,
+        "config": {"workload": workload_name(a), "global_batch": a.batch * world, "micro_batch": eng.micro, "lanes": eng.lanes,
                    "parallelism": "batch-sharded x%d, NCCL all-gather of packed detections" % world if world > 1
                    else "single GPU", "weights": "seeded random init (head biases calibrated to ~1% boxes > 0.2)",
                    "score_threshold": SCORE, "iou_threshold": IOU, "detections_per_step_rank0": n_det,

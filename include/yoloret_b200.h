@@ -108,7 +108,8 @@ typedef struct yr_op {
     int32_t ld_in, ld_in2, ld_in3, ld_in4, ld_out, ld_res;
     int32_t K2, K3, K4;      /* RFCR: channels of in2..in4 */
     int32_t variant;         /* PW kernel choice: 0 = auto (tcgen05 when w_tc is given), 1 = SIMT fp32,
-                                2 = tcgen05 3xTF32 */
+                                2 = tcgen05 3xTF32, A and B operands in shared memory (w_tc = yr_pw_tc_pack image),
+                                3 = tcgen05 3xTF32, A operand in tensor memory (w_tc = yr_pw_ts_pack image) */
     const void* in;
     const void* in2;
     const void* in3;
@@ -118,7 +119,7 @@ typedef struct yr_op {
     const float* bias;
     const float* res;
     const float* scale;
-    const float* w_tc;       /* PW: weight image made by yr_pw_tc_pack (tensor-core variant), or NULL */
+    const float* w_tc;       /* PW: weight image made by yr_pw_tc_pack (variant 0/2) or yr_pw_ts_pack (variant 3), or NULL */
     float* aux;              /* DW: squeeze-excite partial sums (see above), or NULL */
 } yr_op;
 
@@ -141,6 +142,9 @@ int yr_run_ops(const yr_op* ops, int n_ops, void* stream);
  *   yr_pw_tc_pack           packed must be 128-byte aligned */
 int64_t yr_pw_tc_packed_floats(int K, int N);
 int yr_pw_tc_pack(const float* w, int K, int N, float* packed, void* stream);
+/* Same for the variant-3 kernel (its n tiles are at most 192 columns wide, so the image differs). */
+int64_t yr_pw_ts_packed_floats(int K, int N);
+int yr_pw_ts_pack(const float* w, int K, int N, float* packed, void* stream);
 
 /* Fused inverted-residual block (YR_OP_MBCONV): packs the folded weights of its three layers -
  *   w1 [Cin][ld1] + b1[Ce] (expand), wd [9][ldd] + b2[Ce] (depthwise), w2 [Ce][ld2] + b3[Cout] (project) -

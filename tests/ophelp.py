@@ -41,21 +41,23 @@ def pw_op(a, w, bias, act="none", res=None, scale=None, ld_out=None, variant=0):
     if scale is not None:
         op.scale = scale.data_ptr()
     if variant != _lib.PW_SIMT:
-        packed = pack_tc(w)
+        packed = pack_tc(w, variant)
         op.w_tc = packed.data_ptr()
     run_op(op)
     return out
 
 
-def pack_tc(w):
-    """W [K,N] (CUDA) -> the tensor-core weight image (yr_pw_tc_pack)."""
+def pack_tc(w, variant=_lib.PW_TC):
+    """W [K,N] (CUDA) -> the tensor-core weight image (yr_pw_tc_pack; yr_pw_ts_pack for variant 3)."""
     K, N = w.shape
     lib = _lib.lib()
-    n = int(lib.yr_pw_tc_packed_floats(K, N))
+    sizer, packer = ((lib.yr_pw_ts_packed_floats, lib.yr_pw_ts_pack) if variant == _lib.PW_TS
+                     else (lib.yr_pw_tc_packed_floats, lib.yr_pw_tc_pack))
+    n = int(sizer(K, N))
     assert n > 0, "no tensor-core tiling for K=%d N=%d" % (K, N)
     packed = torch.full((n,), float("nan"), device="cuda")
-    _lib.check(lib.yr_pw_tc_pack(w.contiguous().data_ptr(), K, N, packed.data_ptr(),
-                                 torch.cuda.current_stream().cuda_stream), "yr_pw_tc_pack")
+    _lib.check(packer(w.contiguous().data_ptr(), K, N, packed.data_ptr(),
+                      torch.cuda.current_stream().cuda_stream), "yr_pw_pack")
     torch.cuda.synchronize()
     assert not torch.isnan(packed).any()
     return packed

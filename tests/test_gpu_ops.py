@@ -35,8 +35,11 @@ def _rand(*shape, seed=0, scale=1.0):
     (3, 13, 13, 512, 512, 512, "relu6", False, False),  # streamed weights, two n tiles
     (2, 64, 64, 256, 256, 256, "none", True, False),    # widest single n tile, > 1 tile per CTA? (64 tiles)
     (4, 100, 100, 24, 144, 24, "relu6", False, False),  # 313 tiles > 148 CTAs: persistent loop, both accumulators
+    (8, 52, 52, 128, 256, 128, "none", False, False),   # 169 row blocks x 2 n tiles: ring wrap-around of every role
+    (8, 40, 40, 432, 72, 432, "none", True, False),     # streamed weights over many k-blocks and tiles
+    (6, 48, 48, 48, 32, 48, "swish", False, True),      # 4 narrow accumulators, SE gate, 108 tiles
 ])
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_pw_parity(built_lib, B, H, W, K, N, ld_in, act, use_res, use_scale, variant):
     a = _rand(B, H, W, ld_in, seed=1)
     w = _rand(K, N, seed=2, scale=K ** -0.5)
@@ -54,6 +57,27 @@ def test_pw_parity(built_lib, B, H, W, K, N, ld_in, act, use_res, use_scale, var
     got = out[..., :N].cpu().double()
     assert torch.isnan(out[..., N:]).all(), "kernel wrote outside its channel slice"
     torch.testing.assert_close(got, ref, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("B,H,W,K,N,act,use_res,use_scale", [
+    (3, 16, 16, 144, 24, "none", True, False),
+    (2, 26, 26, 424, 256, "relu6", False, False),
+    (2, 13, 13, 512, 80, "none", False, True),
+    (1, 30, 30, 120, 720, "swish", False, False),
+    (4, 100, 100, 24, 144, "relu6", False, False),
+])
+def test_pw_tensor_core_variants_bit_identical(built_lib, B, H, W, K, N, act, use_res, use_scale):
+    """The shared-memory-A (2) and tensor-memory-A (3) tcgen05 kernels issue the same three MMAs per K step in the
+    same order on the same split operands, so the engine's per-layer autotuner may pick either without changing
+    a single output bit."""
+    a = _rand(B, H, W, K, seed=11).cuda()
+    w = _rand(K, N, seed=12, scale=K ** -0.5).cuda()
+    bias = _rand(N, seed=13).cuda()
+    res = _rand(B, H, W, N, seed=14).cuda() if use_res else None
+    scale = torch.rand(B, K, generator=torch.Generator().manual_seed(15)).cuda() if use_scale else None
+    o2 = pw_op(a, w, bias, act, res, scale, variant=2)
+    o3 = pw_op(a, w, bias, act, res, scale, variant=3)
+    assert torch.equal(o2, o3), float((o2 - o3).abs().max())
 
 
 def _same_pad_lead(size, k, s):
@@ -150,8 +174,9 @@ def test_resample_exact(built_lib, mode):
     assert torch.isnan(out[..., :8]).all() and torch.isnan(out[..., 8 + C:]).all()
 
 
-def test_rfcr_parity(built_lib):
-    B, H, W = 2, 6, 10  # stride-16 grid
+@pytest.mark.parametrize("H,W", [(6, 10), (8, 6), (26, 26)])  # 8 rows: ragged last row group of the kernel
+def test_rfcr_parity(built_lib, H, W):
+    B = 2  # H x W = the stride-16 grid
     K1, K2, K3, K4, N = 120, 72, 24, 24, 48
     b1, b2 = _rand(B, H // 2, W // 2, K1, seed=1), _rand(B, H, W, K2, seed=2)
     b3, b4 = _rand(B, 2 * H, 2 * W, K3, seed=3), _rand(B, 4 * H, 4 * W, K4, seed=4)

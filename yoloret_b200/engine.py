@@ -61,7 +61,7 @@ class Engine:
                  weights: Dict[str, np.ndarray], anchors: np.ndarray, micro_batch: Optional[int] = None,
                  num_scales: int = 3, max_boxes: int = 20, cand_cap: Optional[int] = None,
                  device: Optional[torch.device] = None, pw_variant: int = _lib.PW_AUTO, input_u8: bool = False,
-                 fuse_se: bool = True, fuse_mbconv: bool = False):
+                 fuse_se: bool = True, fuse_mbconv: bool = False, lanes: int = 1, autotune: bool = True):
         if not torch.cuda.is_available():
             raise _lib.YrError("yoloret_b200.Engine needs a CUDA device (no CPU fallback exists)")
         self.lib = _lib.lib()
@@ -69,13 +69,22 @@ class Engine:
         self.net = NetDef(model_name, num_classes, input_hw)
         self.model_name, self.num_classes, self.input_hw = model_name, num_classes, tuple(input_hw)
         self.batch = int(batch)
-        self.micro = int(micro_batch) if micro_batch else self.batch
+        # lanes > 1: the micro-batches of a step run concurrently on that many CUDA streams (fork/join inside the
+        # captured graph), each lane on its own activation arena: the small late layers leave most SMs idle when run
+        # alone (a 13x13 layer at batch 64 is 85 tiles for 148 SMs) and overlap with the other lanes' layers instead
+        self.lanes = max(1, int(lanes))
+        if micro_batch:
+            self.micro = int(micro_batch)
+        else:
+            self.micro = (self.batch + self.lanes - 1) // self.lanes
+        self._lane_streams: List[torch.cuda.Stream] = []
         self.num_scales, self.max_boxes = num_scales, max_boxes
         self.anchors = np.asarray(anchors, dtype=np.float32).reshape(-1, 2)
         self.input_u8 = input_u8
         self.pw_variant = pw_variant
         self.fuse_se = fuse_se
         self.fuse_mbconv = fuse_mbconv
+        self.autotune = bool(autotune)
         self.cand_cap_arg = cand_cap
         self._check_weights(weights)
         self._alloc()
@@ -83,6 +92,8 @@ class Engine:
         self._plans: Dict[Tuple[int, int], Tuple] = {}
         self._graph = None
         self.launches_per_forward = 0
+        if self.autotune and self.pw_variant == _lib.PW_AUTO:
+            self._autotune_pw()
 
     # ---- setup -----------------------------------------------------------------
     def _check_weights(self, w):
@@ -102,14 +113,20 @@ class Engine:
             n = self.micro * b.H * b.W * b.ld
             offs[b.name] = total
             total += (n + 63) // 64 * 64
-        self.arena = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.arena = torch.zeros(self.lanes, total, dtype=torch.float32, device=dev)
+        self.lane_buf_t: List[Dict[str, torch.Tensor]] = [dict() for _ in range(self.lanes)]
         for b in net.bufs:
             if b.full_batch:
                 self.buf_t[b.name] = torch.zeros(self.batch, b.H, b.W, b.ld, dtype=torch.float32, device=dev)
+                for lane in range(self.lanes):
+                    self.lane_buf_t[lane][b.name] = self.buf_t[b.name]
             else:
                 n = self.micro * b.H * b.W * b.ld
-                self.buf_t[b.name] = self.arena[offs[b.name]:offs[b.name] + n].view(self.micro, b.H, b.W, b.ld)
-        self.arena_bytes = total * 4
+                for lane in range(self.lanes):
+                    self.lane_buf_t[lane][b.name] = self.arena[lane, offs[b.name]:offs[b.name] + n].view(
+                        self.micro, b.H, b.W, b.ld)
+                self.buf_t[b.name] = self.lane_buf_t[0][b.name]
+        self.arena_bytes = total * 4 * self.lanes
         in_dtype = torch.uint8 if self.input_u8 else torch.float32
         # two input slots: slot 1 exists so a streaming caller can upload batch i+1 while batch i computes
         self.inputs = [torch.zeros(self.batch, self.input_hw[0], self.input_hw[1], 3, dtype=in_dtype, device=dev)]
@@ -125,17 +142,21 @@ class Engine:
     def _prep_weights(self, w):
         """Folds BN, pads channels to the device layout and uploads."""
         self.wdev: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
-        self.wtc: Dict[int, torch.Tensor] = {}   # tensor-core weight images of the pointwise layers
+        self.wtc: Dict[int, torch.Tensor] = {}   # tensor-core weight images of the pointwise layers (SS kernel)
+        self.wts: Dict[int, torch.Tensor] = {}   # ... for the A-in-TMEM kernel (variant 3)
+        self.pw_choice: Dict[int, int] = {}      # per-layer kernel variant (set by the autotuner)
         self.se_fused: Dict[int, bool] = {}      # SE layers whose squeeze rides in the depthwise epilogue
-        self.se_part: Dict[int, torch.Tensor] = {}
+        self.se_part: Dict[Tuple[int, int], torch.Tensor] = {}   # (lane, SE layer) -> per-CTA partial sums
         for i, L in enumerate(self.net.layers):
             if L.kind == "pw":
                 k = w[L.conv + "/kernel"][0, 0].astype(np.float64)          # [Cin, Cout]
                 s, b = _fold_bn(w, L.bn, k.shape[1])
                 mat = _pad_cols(_expand_rows(k * s[None, :], L.inp[0].segs), L.out.C)
                 self.wdev[i] = (self._dev(mat), self._dev(_pad_cols(b, L.out.C)))
-                if self.pw_variant != _lib.PW_SIMT:
-                    self.wtc[i] = self._pack_tc(self.wdev[i][0])
+                if self.pw_variant in (_lib.PW_AUTO, _lib.PW_TC):
+                    self.wtc[i] = self._pack_tc(self.wdev[i][0], _lib.PW_TC)
+                if self.pw_variant in (_lib.PW_AUTO, _lib.PW_TS):
+                    self.wts[i] = self._pack_tc(self.wdev[i][0], _lib.PW_TS)
             elif L.kind == "dw":
                 k = w[L.conv + "/depthwise_kernel"][:, :, :, 0].astype(np.float64)  # [k,k,C]
                 s, b = _fold_bn(w, L.bn, k.shape[2])
@@ -207,17 +228,70 @@ class Engine:
                        "yr_mbconv_pack")
             self.mb_blob[i] = blob
 
-    def _pack_tc(self, w_kn: torch.Tensor) -> Optional[torch.Tensor]:
-        """yr_pw_tc_pack: [K,N] fp32 -> split/swizzled TF32 (hi, lo) image for the tcgen05 kernel."""
+    def _pack_tc(self, w_kn: torch.Tensor, variant: int) -> Optional[torch.Tensor]:
+        """yr_pw_tc_pack / yr_pw_ts_pack: [K,N] fp32 -> split/swizzled TF32 (hi, lo) image for a tcgen05 kernel."""
         K, N = int(w_kn.shape[0]), int(w_kn.shape[1])
-        n = int(self.lib.yr_pw_tc_packed_floats(K, N))
+        sizer, packer = ((self.lib.yr_pw_ts_packed_floats, self.lib.yr_pw_ts_pack) if variant == _lib.PW_TS
+                         else (self.lib.yr_pw_tc_packed_floats, self.lib.yr_pw_tc_pack))
+        n = int(sizer(K, N))
         if n <= 0:
-            if self.pw_variant == _lib.PW_TC:
+            if self.pw_variant == variant:
                 raise _lib.YrError("no tensor-core tiling for a %dx%d pointwise layer" % (K, N))
-            return None  # auto: this layer stays on the exact-fp32 SIMT kernel
+            return None  # auto: this layer stays on another kernel (the exact-fp32 SIMT one if neither fits)
         packed = torch.empty(n, dtype=torch.float32, device=self.device)
-        _lib.check(self.lib.yr_pw_tc_pack(w_kn.data_ptr(), K, N, packed.data_ptr(), self._stream()), "yr_pw_tc_pack")
+        _lib.check(packer(w_kn.data_ptr(), K, N, packed.data_ptr(), self._stream()), "yr_pw_pack")
         return packed
+
+    def _pw_variant_of(self, i: int) -> int:
+        """Kernel variant layer ``i`` runs with (explicit engine setting, else the autotuner's pick, else the
+        first tensor-core kernel that has a tiling, else SIMT)."""
+        if self.pw_variant != _lib.PW_AUTO:
+            return self.pw_variant
+        if i in self.pw_choice:
+            return self.pw_choice[i]
+        if self.wtc.get(i) is not None:
+            return _lib.PW_TC
+        if self.wts.get(i) is not None:
+            return _lib.PW_TS
+        return _lib.PW_SIMT
+
+    def _autotune_pw(self, reps: int = 3):
+        """Picks, per pointwise layer, the faster of the two tcgen05 kernels (shared-memory A vs tensor-memory A)
+        by timing both on the layer's real buffers with CUDA events.  The two kernels issue the same MMAs in
+        the same order and give bit-identical outputs (tests/test_gpu_ops.py), so the pick changes speed only."""
+        both = [i for i, L in enumerate(self.net.layers)
+                if L.kind == "pw" and self.wtc.get(i) is not None and self.wts.get(i) is not None]
+        if not both:
+            return
+        nb = min(self.micro, self.batch)
+        ops, cnt = self.build_plan(0, nb)
+        op_of = {li: k for k, (_kind, _name, _b, _f, li) in enumerate(self._plan_meta)}
+        st = self._stream()
+        cache: Dict[Tuple, int] = {}
+        self.autotune_log: List[Tuple] = []
+        for i in both:
+            if i not in op_of:
+                continue
+            L = self.net.layers[i]
+            key = (L.inp[0].H, L.inp[0].W, L.inp[0].C, L.out.C, L.inp[0].buf.ld, L.out.buf.ld, L.res is not None,
+                   L.gate is not None, L.act)
+            if key not in cache:
+                o = ops[op_of[i]]
+                t = {}
+                for v, img in ((_lib.PW_TC, self.wtc[i]), (_lib.PW_TS, self.wts[i])):
+                    o.variant, o.w_tc = v, img.data_ptr()
+                    _lib.check(self.lib.yr_run_ops(C.byref(o), 1, st), "yr_run_ops")
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(reps):
+                        _lib.check(self.lib.yr_run_ops(C.byref(o), 1, st), "yr_run_ops")
+                    e1.record()
+                    torch.cuda.synchronize(self.device)
+                    t[v] = e0.elapsed_time(e1) / reps
+                cache[key] = _lib.PW_TS if t[_lib.PW_TS] < t[_lib.PW_TC] else _lib.PW_TC
+                self.autotune_log.append((L.name, key[:4], round(t[_lib.PW_TC] * 1e3, 1), round(t[_lib.PW_TS] * 1e3, 1)))
+            self.pw_choice[i] = cache[key]
+        self._plans.clear()  # plans were built with the provisional variants
 
     # ---- plan ---------------------------------------------------------------------
     def input_slot(self, slot: int) -> torch.Tensor:
@@ -225,19 +299,23 @@ class Engine:
             self.inputs.append(torch.zeros_like(self.inputs[0]))
         return self.inputs[slot]
 
-    def _ptr(self, v: View, chunk0: int, slot: int = 0) -> int:
-        """Device address of a view for the micro-batch starting at image ``chunk0``."""
-        t = self.input_slot(slot) if v.buf.name == "input" else self.buf_t[v.buf.name]
+    def _ptr(self, v: View, chunk0: int, slot: int = 0, lane: int = 0) -> int:
+        """Device address of a view for the micro-batch starting at image ``chunk0`` (arena of ``lane``)."""
+        t = self.input_slot(slot) if v.buf.name == "input" else self.lane_buf_t[lane][v.buf.name]
         base = t.data_ptr() + v.off * t.element_size()
         if v.buf.full_batch:
             base += chunk0 * v.buf.H * v.buf.W * v.buf.ld * t.element_size()
         return base
 
-    def build_plan(self, chunk0: int, nb: int, slot: int = 0):
-        """yr_op array for images [chunk0, chunk0+nb) reading input slot ``slot``."""
-        key = (chunk0, nb, slot)
+    def build_plan(self, chunk0: int, nb: int, slot: int = 0, lane: int = 0):
+        """yr_op array for images [chunk0, chunk0+nb) reading input slot ``slot``, activations in arena ``lane``."""
+        key = (chunk0, nb, slot, lane)
         if key in self._plans:
             return self._plans[key]
+        _ptr0 = self._ptr
+
+        def _ptr(v, c0, sl=0):
+            return _ptr0(v, c0, sl, lane)
         ops = (YrOp * len(self.net.layers))()
         gate_ptr: Dict[int, int] = {}
         meta = []   # per emitted op: (kind, name, algorithmic bytes / image, flops / image, layer index)
@@ -259,11 +337,11 @@ class Engine:
                 o.k, o.stride = 3, d.stride
                 o.pad_t, o.pad_l = d.extra.get("pad_t", 0), d.extra.get("pad_l", 0)
                 o.ld_in, o.ld_out = x.buf.ld, b.out.buf.ld
-                o.in_ = self._ptr(x, chunk0, slot)
-                o.out = self._ptr(b.out, chunk0)
+                o.in_ = _ptr(x, chunk0, slot)
+                o.out = _ptr(b.out, chunk0)
                 o.w_tc = self.mb_blob[i].data_ptr()
                 if b.res is not None:
-                    o.res, o.ld_res = self._ptr(b.res, chunk0), b.res.buf.ld
+                    o.res, o.ld_res = _ptr(b.res, chunk0), b.res.buf.ld
                 fused_bytes = 4 * (x.H * x.W * x.Clog + b.out.H * b.out.W * b.out.Clog * (2 if b.res is not None else 1)) \
                     + self.mb_blob[i].numel() * 4
                 meta.append(("mbconv", L.name.replace("_expand", "") + "_fused", fused_bytes, L.flops + d.flops + b.flops, i))
@@ -276,8 +354,8 @@ class Engine:
             o.k, o.stride = L.k, L.stride
             o.pad_t, o.pad_l = L.extra.get("pad_t", 0), L.extra.get("pad_l", 0)
             o.ld_in, o.ld_out = x.buf.ld, L.out.buf.ld
-            o.in_ = self._ptr(x, chunk0, slot)
-            o.out = self._ptr(L.out, chunk0)
+            o.in_ = _ptr(x, chunk0, slot)
+            o.out = _ptr(L.out, chunk0)
             if i in self.wdev:
                 o.w, o.bias = self.wdev[i][0].data_ptr(), self.wdev[i][1].data_ptr()
             if L.kind == "stem":
@@ -286,22 +364,24 @@ class Engine:
                 o.in_is_u8 = 1 if self.input_u8 else 0
             elif L.kind == "pw":
                 o.kind = _lib.OP_PW
-                o.variant = self.pw_variant
-                if self.wtc.get(i) is not None:
-                    o.w_tc = self.wtc[i].data_ptr()
+                o.variant = self._pw_variant_of(i)
+                img = (self.wts if o.variant == _lib.PW_TS else self.wtc).get(i)
+                if o.variant != _lib.PW_SIMT and img is not None:
+                    o.w_tc = img.data_ptr()
                 if L.res is not None:
-                    o.res, o.ld_res = self._ptr(L.res, chunk0), L.res.buf.ld
+                    o.res, o.ld_res = _ptr(L.res, chunk0), L.res.buf.ld
                 if L.gate is not None:
                     o.scale = gate_ptr[id(L.gate)]
             elif L.kind == "dw":
                 o.kind = _lib.OP_DW
                 if self.se_fused.get(i + 1):
-                    if i + 1 not in self.se_part:
+                    if (lane, i + 1) not in self.se_part:
                         slots = int(self.lib.yr_dw_se_slots(C.byref(o)))
                         if slots <= 0:
                             _lib.check(slots, "yr_dw_se_slots")
-                        self.se_part[i + 1] = torch.zeros(self.micro, slots, o.C, dtype=torch.float32, device=self.device)
-                    o.aux = self.se_part[i + 1].data_ptr()
+                        self.se_part[(lane, i + 1)] = torch.zeros(self.micro, slots, o.C, dtype=torch.float32,
+                                                                  device=self.device)
+                    o.aux = self.se_part[(lane, i + 1)].data_ptr()
             elif L.kind == "resample":
                 o.kind = _lib.OP_RESAMPLE
                 o.mode = _MODE[L.mode]
@@ -311,14 +391,14 @@ class Engine:
                 gate_ptr[id(L)] = o.out
                 if self.se_fused.get(i):
                     o.kind = _lib.OP_SE_FC
-                    o.in_ = self.se_part[i].data_ptr()
-                    o.K2 = int(self.se_part[i].shape[1])
+                    o.in_ = self.se_part[(lane, i)].data_ptr()
+                    o.K2 = int(self.se_part[(lane, i)].shape[1])
             elif L.kind == "rfcr":
                 o.kind = _lib.OP_RFCR
                 b1, b2, b3, b4 = L.inp
                 o.C, o.K2, o.K3, o.K4 = b1.C, b2.C, b3.C, b4.C
                 o.ld_in, o.ld_in2, o.ld_in3, o.ld_in4 = b1.buf.ld, b2.buf.ld, b3.buf.ld, b4.buf.ld
-                o.in_, o.in2, o.in3, o.in4 = (self._ptr(v, chunk0) for v in (b1, b2, b3, b4))
+                o.in_, o.in2, o.in3, o.in4 = (_ptr(v, chunk0) for v in (b1, b2, b3, b4))
             else:
                 raise ValueError(L.kind)
         self._plans[key] = (ops, n_ops)
@@ -331,13 +411,33 @@ class Engine:
 
     def run_network(self, slot: int = 0):
         """yolov3_body forward over input slot ``slot`` -> y buffers, micro-batch by micro-batch."""
-        st = self._stream()
+        chunks = [(c0, min(self.micro, self.batch - c0)) for c0 in range(0, self.batch, self.micro)]
         n = 0
-        for c0 in range(0, self.batch, self.micro):
-            nb = min(self.micro, self.batch - c0)
-            ops, cnt = self.build_plan(c0, nb, slot)
-            _lib.check(self.lib.yr_run_ops(ops, cnt, st), "yr_run_ops")
-            n += cnt
+        if self.lanes == 1 or len(chunks) == 1:
+            st = self._stream()
+            for c0, nb in chunks:
+                ops, cnt = self.build_plan(c0, nb, slot)
+                _lib.check(self.lib.yr_run_ops(ops, cnt, st), "yr_run_ops")
+                n += cnt
+            return n
+        # fork: every lane's stream waits for the caller's stream, runs its micro-batches in order on its own arena,
+        # and the caller's stream joins them all (under graph capture this becomes a fork/join sub-graph)
+        main = torch.cuda.current_stream(self.device)
+        while len(self._lane_streams) < self.lanes:
+            self._lane_streams.append(torch.cuda.Stream(self.device))
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for lane in range(self.lanes):
+            ls = self._lane_streams[lane]
+            ls.wait_event(fork)
+            for j in range(lane, len(chunks), self.lanes):
+                c0, nb = chunks[j]
+                ops, cnt = self.build_plan(c0, nb, slot, lane)
+                _lib.check(self.lib.yr_run_ops(ops, cnt, ls.cuda_stream), "yr_run_ops")
+                n += cnt
+            done = torch.cuda.Event()
+            done.record(ls)
+            main.wait_event(done)
         return n
 
     def raw_outputs(self) -> List[torch.Tensor]:
