@@ -123,7 +123,9 @@ def test_dw_parity(built_lib, B, H, W, C, k, s, act):
 
 
 @pytest.mark.parametrize("u8", [False, True])
-@pytest.mark.parametrize("H,W,N,act", [(32, 32, 24, "relu6"), (33, 47, 40, "swish")])
+@pytest.mark.parametrize("H,W,N,act", [(32, 32, 24, "relu6"), (33, 47, 40, "swish"),  # odd size: the generic kernel
+                                       (96, 160, 24, "relu6"), (70, 52, 48, "relu6"), (37, 44, 32, "swish"),
+                                       (416, 416, 24, "relu6")])
 def test_stem_parity(built_lib, u8, H, W, N, act):
     B = 2
     g = torch.Generator().manual_seed(0)

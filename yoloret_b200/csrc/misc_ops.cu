@@ -124,6 +124,172 @@ stem_kernel_v2(const void* __restrict__ in_, const float* __restrict__ wgt, cons
     }
 }
 
+// v3 (stride 2): the CTA stages the 2*TH+1 input rows its TH output rows need in shared memory with fully
+// coalesced 128-bit loads (a row of the NHWC image with C = 3 is one contiguous run), then a thread owns
+// 4 consecutive output pixels x CPT channels: per input row it reads its 27 taps as 7 LDS.128 and reuses every
+// weight float4 (a shared-memory broadcast) for 4 pixels, so the loop is ~13 FMAs per shared-memory access
+// instead of 4 (v2) and the HBM side is pure streaming.  FMA order per output = v2's: (kh, kw, ci) ascending.
+constexpr int STEM_ROUNDS = 3;
+
+template <int ACT, bool U8, int CPT>
+__global__ void __launch_bounds__(512)
+stem_kernel_v3(const void* __restrict__ in_, const float* __restrict__ wgt, const float* __restrict__ bias,
+               float* __restrict__ out, int ld_out, int H, int W, int Ho, int Wo, int N, int pad_t, int pad_l, int TH,
+               int row_floats) {
+    extern __shared__ __align__(16) float sm3[];
+    float* sw = sm3;                       // [27][N]
+    float* sx = sm3 + ((27 * N + 3) & ~3);  // [2*TH+1][row_floats]: pad_l zero pixels, the row, zero tail
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int b = blockIdx.y, ho0 = blockIdx.x * TH;
+    const int in_rows = 2 * TH + 1;
+    for (int i = tid; i < 27 * N; i += nt) sw[i] = wgt[i];
+    // one warp per 32-chunk segment of a row: zero pads / out-of-image rows, copy the rest (16 bytes per lane;
+    // fp32 rows that start 16-byte aligned in shared memory go through cp.async, no register round trip)
+    const int lead = pad_l * 3, body = W * 3;
+    const int q = body >> 2;                 // 16-byte (fp32) or 4-byte (u8) chunks per row; W % 4 == 0
+    const int segs = (q + 31) >> 5;
+    const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+    // The TH output rows are computed in STEM_ROUNDS rounds of RPR rows; the input rows of every round are
+    // requested up front, one cp.async group per round, so round j computes while the rows of j+1.. are in flight.
+    const int RPR = TH / STEM_ROUNDS;
+    auto stage_rows = [&](int r_begin, int r_end) {
+        for (int sg = warp + r_begin * segs; sg < r_end * segs; sg += nwarps) {
+            const int r = sg / segs, c4 = (sg - r * segs) * 32 + lane;
+            const int hi = ho0 * 2 - pad_t + r;
+            float* drow = sx + r * row_floats;
+            if (hi < 0 || hi >= H) {
+                for (int c = (sg - r * segs) * 128 + lane; c < min(row_floats, (sg - r * segs + 1) * 128); c += 32) drow[c] = 0.0f;
+                if (sg - r * segs == segs - 1)
+                    for (int c = segs * 128 + lane; c < row_floats; c += 32) drow[c] = 0.0f;
+                continue;
+            }
+            if (sg - r * segs == 0) {  // pads of a valid row
+                for (int c = lane; c < lead; c += 32) drow[c] = 0.0f;
+                for (int c = lead + body + lane; c < row_floats; c += 32) drow[c] = 0.0f;
+            }
+            if (c4 >= q) continue;
+            if (U8) {
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(in_) + ((size_t)b * H + hi) * body;
+                const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src + c4 * 4));
+                float* d = drow + lead + c4 * 4;
+                d[0] = (float)(v & 0xffu) * (1.0f / 255.0f);
+                d[1] = (float)((v >> 8) & 0xffu) * (1.0f / 255.0f);
+                d[2] = (float)((v >> 16) & 0xffu) * (1.0f / 255.0f);
+                d[3] = (float)(v >> 24) * (1.0f / 255.0f);
+            } else {
+                const float* src = reinterpret_cast<const float*>(in_) + ((size_t)b * H + hi) * body + c4 * 4;
+                float* d = drow + lead + c4 * 4;
+                if (lead == 0) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(d)), "l"(src)
+                                 : "memory");
+                } else {  // lead is a multiple of 3 floats: destination not 16-byte aligned
+                    const float4 v = ldg4(src);
+                    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage_rows(0, 2 * RPR + 1);
+#pragma unroll
+    for (int j = 1; j < STEM_ROUNDS; ++j) stage_rows(2 * RPR * j + 1, 2 * RPR * (j + 1) + 1);
+
+    const int NCG = N / CPT;
+    const int groups = (Wo + 3) >> 2;
+    const int items = RPR * groups * NCG;
+#pragma unroll
+    for (int round = 0; round < STEM_ROUNDS; ++round) {
+    if (round == 0) asm volatile("cp.async.wait_group %0;" ::"n"(STEM_ROUNDS - 1) : "memory");
+    else if (round == STEM_ROUNDS - 1) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    else asm volatile("cp.async.wait_group %0;" ::"n"(STEM_ROUNDS - 2) : "memory");
+    __syncthreads();
+    for (int item = tid; item < items; item += nt) {
+        const int cg = item % NCG;
+        const int g = (item / NCG) % groups;
+        const int r = round * RPR + item / (NCG * groups);
+        const int ho = ho0 + r;
+        if (ho >= Ho) break;
+        const int n = cg * CPT;
+        float acc[4][CPT];
+#pragma unroll
+        for (int px = 0; px < 4; ++px)
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) acc[px][j] = 0.0f;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            float x[28];
+            const float4* xr = reinterpret_cast<const float4*>(sx + (2 * r + kh) * row_floats + g * 24);
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                const float4 v = xr[i];
+                x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+            }
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) {
+                    const float* wp = sw + ((kh * 3 + kw) * 3 + ci) * N + n;
+#pragma unroll
+                    for (int j4 = 0; j4 < CPT / 4; ++j4) {
+                        const float4 wv = *reinterpret_cast<const float4*>(wp + j4 * 4);
+#pragma unroll
+                        for (int px = 0; px < 4; ++px) {
+                            const float xv = x[(2 * px + kw) * 3 + ci];
+                            acc[px][j4 * 4 + 0] = fmaf(xv, wv.x, acc[px][j4 * 4 + 0]);
+                            acc[px][j4 * 4 + 1] = fmaf(xv, wv.y, acc[px][j4 * 4 + 1]);
+                            acc[px][j4 * 4 + 2] = fmaf(xv, wv.z, acc[px][j4 * 4 + 2]);
+                            acc[px][j4 * 4 + 3] = fmaf(xv, wv.w, acc[px][j4 * 4 + 3]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+            const int wo = g * 4 + px;
+            if (wo >= Wo) break;
+            float* o = out + (((size_t)b * Ho + ho) * Wo + wo) * ld_out + n;
+#pragma unroll
+            for (int j4 = 0; j4 < CPT / 4; ++j4) {
+                const float4 bv = ldg4(bias + n + j4 * 4);
+                float4 v;
+                v.x = apply_act<ACT>(acc[px][j4 * 4 + 0] + bv.x);
+                v.y = apply_act<ACT>(acc[px][j4 * 4 + 1] + bv.y);
+                v.z = apply_act<ACT>(acc[px][j4 * 4 + 2] + bv.z);
+                v.w = apply_act<ACT>(acc[px][j4 * 4 + 3] + bv.w);
+                st4(o + j4 * 4, v);
+            }
+        }
+    }
+    }
+}
+
+template <int ACT, bool U8, int CPT>
+static bool launch_stem_v3(const yr_op& op, cudaStream_t s) {
+    if (op.stride != 2 || op.W % 4 != 0 || op.B > 65535) return false;
+    const int row_items = cdiv(op.Wo, 4) * (op.N / CPT);
+    if (row_items > 512) return false;
+    const int rows_per_round = 384 / row_items > 0 ? 384 / row_items : 1;
+    const int threads = (rows_per_round * row_items + 31) / 32 * 32;
+    const int TH = rows_per_round * STEM_ROUNDS;
+    // a thread reads 28 floats from float offset 24*g of its rows: the row needs 24*(groups-1) + 28 floats
+    int row_floats = (op.pad_l + op.W) * 3;
+    const int need = 24 * (cdiv(op.Wo, 4) - 1) + 28;
+    if (row_floats < need) row_floats = need;
+    row_floats = (row_floats + 3) & ~3;
+    const size_t smem = ((size_t)((27 * op.N + 3) & ~3) + (size_t)(2 * TH + 1) * row_floats) * sizeof(float);
+    if (smem > 160 * 1024) return false;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(stem_kernel_v3<ACT, U8, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr_set = true;
+    }
+    dim3 grid(cdiv(op.Ho, TH), op.B);
+    stem_kernel_v3<ACT, U8, CPT><<<grid, threads, smem, s>>>(op.in, op.w, op.bias, (float*)op.out, op.ld_out, op.H, op.W,
+                                                              op.Ho, op.Wo, op.N, op.pad_t, op.pad_l, TH, row_floats);
+    return true;
+}
+
 template <int ACT, bool U8, int CPT>
 static void launch_stem_v2(const yr_op& op, cudaStream_t s) {
     const long long total = (long long)op.B * op.Ho * op.Wo * (op.N / CPT);
@@ -138,7 +304,9 @@ static int launch_stem_act(const yr_op& op, cudaStream_t s) {
     const long long total = (long long)op.B * op.Ho * op.Wo * (op.N / 4);
     const unsigned grid = (unsigned)((total + 255) / 256);
     const size_t smem = (size_t)27 * op.N * sizeof(float);
-    if (op.N % 12 == 0) {
+    // v3 with 4 channels per thread: the N/4 lanes of a pixel store one contiguous run (full 32-byte sectors)
+    if (op.in_is_u8 ? launch_stem_v3<ACT, true, 4>(op, s) : launch_stem_v3<ACT, false, 4>(op, s)) {
+    } else if (op.N % 12 == 0) {
         if (op.in_is_u8) launch_stem_v2<ACT, true, 12>(op, s);
         else launch_stem_v2<ACT, false, 12>(op, s);
     } else if (op.N % 8 == 0) {
@@ -235,8 +403,23 @@ int launch_resample(const yr_op& op, cudaStream_t s) {
 // conv-then-pool for b3, pool-then-conv for b4, adds left to right, as the reference.
 // One CTA = RF_PIX consecutive output pixels of a row; inputs staged in shared memory.
 // ---------------------------------------------------------------------------------
-// One CTA = one output row: the stacked 1x1 kernels (K1+K2+K3+K4 rows of N) and the row's inputs are
-// staged in shared memory once, then every thread owns (pixel, 4 output channels) items.
+// One CTA = RFCR_ROWS output rows of one image.  The stacked 1x1 kernels (K1+K2+K3+K4 rows of N) and the
+// 4x4-max-pooled b4 rows are staged in shared memory once per CTA; a thread owns an item of
+// (2 horizontally adjacent output pixels) x (8 output channels): the two pixels share their b1 pixel, every
+// weight float4 read from shared memory feeds both, and the activations come straight from global memory as
+// float4 over k (they are L1/L2 resident: the 6 channel groups of a pixel pair read the same lines).
+// Each dot product keeps the single-accumulator, ascending-k FMA order of a plain 1x1 convolution.
+constexpr int RFCR_ROWS = 3;
+
+__device__ __forceinline__ void fma8(float (&acc)[8], float x, const float* w) {
+    const float4 w0 = *reinterpret_cast<const float4*>(w);
+    const float4 w1 = *reinterpret_cast<const float4*>(w + 4);
+    acc[0] = fmaf(x, w0.x, acc[0]); acc[1] = fmaf(x, w0.y, acc[1]);
+    acc[2] = fmaf(x, w0.z, acc[2]); acc[3] = fmaf(x, w0.w, acc[3]);
+    acc[4] = fmaf(x, w1.x, acc[4]); acc[5] = fmaf(x, w1.y, acc[5]);
+    acc[6] = fmaf(x, w1.z, acc[6]); acc[7] = fmaf(x, w1.w, acc[7]);
+}
+
 __global__ void __launch_bounds__(256)
 rfcr_kernel(const float* __restrict__ b1, int ld1, int K1, const float* __restrict__ b2, int ld2, int K2,
             const float* __restrict__ b3, int ld3, int K3, const float* __restrict__ b4, int ld4, int K4,
@@ -245,95 +428,121 @@ rfcr_kernel(const float* __restrict__ b1, int ld1, int K1, const float* __restri
     extern __shared__ __align__(16) float sm[];
     const int KT = K1 + K2 + K3 + K4;
     const int W1 = W >> 1, H1 = H >> 1;
-    float* sw = sm;                      // [KT][N]
-    float* s1 = sw + (size_t)KT * N;     // [W1][K1]
-    float* s2 = s1 + W1 * K1;            // [W][K2]
-    float* s3 = s2 + W * K2;             // [W][4][K3]
-    float* s4 = s3 + W * 4 * K3;         // [W][K4]   (4x4 max-pooled b4)
-    const int h = blockIdx.x, b = blockIdx.y;
+    float* sw = sm;                     // [KT][N]
+    float* s4 = sw + (size_t)KT * N;    // [RFCR_ROWS][W][K4]   (4x4 max-pooled b4)
+    const int h0 = blockIdx.x * RFCR_ROWS, b = blockIdx.y;
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int rows = min(RFCR_ROWS, H - h0);
 
     for (int i = tid; i < KT * N / 4; i += nt) st4(sw + i * 4, ldg4(wgt + (size_t)i * 4));
-    for (int i = tid; i < W1 * (K1 / 4); i += nt) {
-        const int p = i / (K1 / 4), k = (i % (K1 / 4)) * 4;
-        st4(s1 + p * K1 + k, ldg4(b1 + (((size_t)b * H1 + (h >> 1)) * W1 + p) * ld1 + k));
-    }
-    for (int i = tid; i < W * (K2 / 4); i += nt) {
-        const int p = i / (K2 / 4), k = (i % (K2 / 4)) * 4;
-        st4(s2 + p * K2 + k, ldg4(b2 + (((size_t)b * H + h) * W + p) * ld2 + k));
-    }
-    for (int i = tid; i < W * 4 * (K3 / 4); i += nt) {
-        const int k = (i % (K3 / 4)) * 4;
-        const int q = (i / (K3 / 4)) % 4, p = i / (K3 / 4) / 4;
-        st4(s3 + (p * 4 + q) * K3 + k,
-            ldg4(b3 + (((size_t)b * 2 * H + 2 * h + (q >> 1)) * (2 * W) + 2 * p + (q & 1)) * ld3 + k));
-    }
-    for (int i = tid; i < W * (K4 / 4); i += nt) {
-        const int p = i / (K4 / 4), k = (i % (K4 / 4)) * 4;
-        const float* base = b4 + (((size_t)b * 4 * H + 4 * h) * (4 * W) + 4 * p) * ld4 + k;
+    for (int i = tid; i < rows * W * (K4 / 4); i += nt) {
+        const int k = (i % (K4 / 4)) * 4;
+        const int p = (i / (K4 / 4)) % W, r = i / (K4 / 4) / W;
+        const float* base = b4 + (((size_t)b * 4 * H + 4 * (h0 + r)) * (4 * W) + 4 * p) * ld4 + k;
         float4 v = ldg4(base);
 #pragma unroll
         for (int y = 0; y < 4; ++y)
 #pragma unroll
             for (int x = 0; x < 4; ++x)
                 if (y | x) v = max4(v, ldg4(base + ((size_t)y * 4 * W + x) * ld4));
-        st4(s4 + p * K4 + k, v);
+        st4(s4 + ((size_t)r * W + p) * K4 + k, v);
     }
     __syncthreads();
 
-    const int N4 = N >> 2;
+    const int NG = N >> 3;
     const float a0 = __ldg(alpha), a1 = __ldg(alpha + 1), a2 = __ldg(alpha + 2), a3 = __ldg(alpha + 3);
     const float* w1p = sw;
     const float* w2p = w1p + (size_t)K1 * N;
     const float* w3p = w2p + (size_t)K2 * N;
     const float* w4p = w3p + (size_t)K3 * N;
-    for (int item = tid; item < W * N4; item += nt) {
-        const int p = item / N4, n = (item % N4) * 4;
-        auto dot = [&](const float* x, const float* wk, int K) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-            for (int k = 0; k < K; ++k) {
-                const float xv = x[k];
-                const float4 wv = *reinterpret_cast<const float4*>(wk + (size_t)k * N + n);
-                a.x = fmaf(xv, wv.x, a.x);
-                a.y = fmaf(xv, wv.y, a.y);
-                a.z = fmaf(xv, wv.z, a.z);
-                a.w = fmaf(xv, wv.w, a.w);
+    for (int item = tid; item < rows * W1 * NG; item += nt) {
+        const int n = (item % NG) * 8;
+        const int pp = (item / NG) % W1, r = item / NG / W1;
+        const int h = h0 + r, p0 = 2 * pp;
+
+        float c1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // W1 . b1[h/2, w/2]: shared by both pixels
+        {
+            const float* x = b1 + (((size_t)b * H1 + (h >> 1)) * W1 + pp) * ld1;
+            for (int k = 0; k < K1; k += 4) {
+                const float4 xv = ldg4(x + k);
+                const float* w = w1p + (size_t)k * N + n;
+                fma8(c1, xv.x, w); fma8(c1, xv.y, w + N); fma8(c1, xv.z, w + 2 * N); fma8(c1, xv.w, w + 3 * N);
             }
-            return a;
-        };
-        const float4 c1 = dot(s1 + (p >> 1) * K1, w1p, K1);
-        const float4 c2 = dot(s2 + p * K2, w2p, K2);
-        float4 c3 = dot(s3 + (p * 4 + 0) * K3, w3p, K3);
-        c3 = max4(c3, dot(s3 + (p * 4 + 1) * K3, w3p, K3));
-        c3 = max4(c3, dot(s3 + (p * 4 + 2) * K3, w3p, K3));
-        c3 = max4(c3, dot(s3 + (p * 4 + 3) * K3, w3p, K3));
-        const float4 c4 = dot(s4 + p * K4, w4p, K4);
-        float4 v;  // ((a0*x0 + a1*x1) + a2*x2) + a3*x3, no FMA contraction across the adds
-        v.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a0, c1.x), __fmul_rn(a1, c2.x)), __fmul_rn(a2, c3.x)), __fmul_rn(a3, c4.x));
-        v.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a0, c1.y), __fmul_rn(a1, c2.y)), __fmul_rn(a2, c3.y)), __fmul_rn(a3, c4.y));
-        v.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a0, c1.z), __fmul_rn(a1, c2.z)), __fmul_rn(a2, c3.z)), __fmul_rn(a3, c4.z));
-        v.w = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a0, c1.w), __fmul_rn(a1, c2.w)), __fmul_rn(a2, c3.w)), __fmul_rn(a3, c4.w));
-        st4(out + (((size_t)b * H + h) * W + p) * ld_out + n, v);
+        }
+        float c2[2][8], c3[2][8], c4[2][8];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) c2[j][i] = c4[j][i] = 0.f;
+        {
+            const float* x = b2 + (((size_t)b * H + h) * W + p0) * ld2;
+            for (int k = 0; k < K2; k += 4) {
+                const float4 xa = ldg4(x + k), xb = ldg4(x + ld2 + k);
+                const float* w = w2p + (size_t)k * N + n;
+                fma8(c2[0], xa.x, w); fma8(c2[0], xa.y, w + N); fma8(c2[0], xa.z, w + 2 * N); fma8(c2[0], xa.w, w + 3 * N);
+                fma8(c2[1], xb.x, w); fma8(c2[1], xb.y, w + N); fma8(c2[1], xb.z, w + 2 * N); fma8(c2[1], xb.w, w + 3 * N);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {   // max_{2x2}(W3 . b3): conv-then-pool, sub-pixel order (0,0),(0,1),(1,0),(1,1)
+            float d[4][8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) d[q][i] = 0.f;
+            const float* x = b3 + (((size_t)b * 2 * H + 2 * h) * (2 * W) + 2 * (p0 + j)) * ld3;
+            const size_t rs = (size_t)2 * W * ld3;
+            for (int k = 0; k < K3; k += 4) {
+                const float4 x0 = ldg4(x + k), x1 = ldg4(x + ld3 + k), x2 = ldg4(x + rs + k), x3 = ldg4(x + rs + ld3 + k);
+                const float* w = w3p + (size_t)k * N + n;
+                fma8(d[0], x0.x, w); fma8(d[0], x0.y, w + N); fma8(d[0], x0.z, w + 2 * N); fma8(d[0], x0.w, w + 3 * N);
+                fma8(d[1], x1.x, w); fma8(d[1], x1.y, w + N); fma8(d[1], x1.z, w + 2 * N); fma8(d[1], x1.w, w + 3 * N);
+                fma8(d[2], x2.x, w); fma8(d[2], x2.y, w + N); fma8(d[2], x2.z, w + 2 * N); fma8(d[2], x2.w, w + 3 * N);
+                fma8(d[3], x3.x, w); fma8(d[3], x3.y, w + N); fma8(d[3], x3.z, w + 2 * N); fma8(d[3], x3.w, w + 3 * N);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) c3[j][i] = fmaxf(fmaxf(fmaxf(d[0][i], d[1][i]), d[2][i]), d[3][i]);
+        }
+        {
+            const float* x = s4 + ((size_t)r * W + p0) * K4;
+            for (int k = 0; k < K4; k += 4) {
+                const float4 xa = *reinterpret_cast<const float4*>(x + k), xb = *reinterpret_cast<const float4*>(x + K4 + k);
+                const float* w = w4p + (size_t)k * N + n;
+                fma8(c4[0], xa.x, w); fma8(c4[0], xa.y, w + N); fma8(c4[0], xa.z, w + 2 * N); fma8(c4[0], xa.w, w + 3 * N);
+                fma8(c4[1], xb.x, w); fma8(c4[1], xb.y, w + N); fma8(c4[1], xb.z, w + 2 * N); fma8(c4[1], xb.w, w + 3 * N);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float v[8];  // ((a0*x0 + a1*x1) + a2*x2) + a3*x3, no FMA contraction across the adds (WeightedSum, model.py:117-137)
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                v[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a0, c1[i]), __fmul_rn(a1, c2[j][i])), __fmul_rn(a2, c3[j][i])),
+                                 __fmul_rn(a3, c4[j][i]));
+            float* o = out + (((size_t)b * H + h) * W + p0 + j) * ld_out + n;
+            st4(o, make_float4(v[0], v[1], v[2], v[3]));
+            st4(o + 4, make_float4(v[4], v[5], v[6], v[7]));
+        }
     }
 }
 
 int launch_rfcr(const yr_op& op, cudaStream_t s) {
     YR_CHECK_ARG(op.in && op.in2 && op.in3 && op.in4 && op.out && op.w && op.bias, "rfcr: null pointer");
     const int K1 = op.C, K2 = op.K2, K3 = op.K3, K4 = op.K4, N = op.N;
-    YR_CHECK_ARG(K1 % 4 == 0 && K2 % 4 == 0 && K3 % 4 == 0 && K4 % 4 == 0 && N % 4 == 0, "rfcr: channels must be multiples of 4");
+    YR_CHECK_ARG(K1 % 4 == 0 && K2 % 4 == 0 && K3 % 4 == 0 && K4 % 4 == 0 && N % 8 == 0, "rfcr: K must be multiples of 4, N of 8");
+    YR_CHECK_ARG(op.ld_in % 4 == 0 && op.ld_in2 % 4 == 0 && op.ld_in3 % 4 == 0 && op.ld_in4 % 4 == 0 && op.ld_out % 4 == 0,
+                 "rfcr: row strides must be multiples of 4");
     YR_CHECK_ARG(op.Ho % 2 == 0 && op.Wo % 2 == 0, "rfcr: output grid must be even");
     YR_CHECK_ARG(op.B <= 65535, "rfcr: batch too large");
     const int W = op.Wo;
-    const size_t smem = ((size_t)(K1 + K2 + K3 + K4) * N + (size_t)(W / 2) * K1 + (size_t)W * K2 + (size_t)W * 4 * K3 +
-                         (size_t)W * K4) * sizeof(float);
+    const size_t smem = ((size_t)(K1 + K2 + K3 + K4) * N + (size_t)RFCR_ROWS * W * K4) * sizeof(float);
     YR_CHECK_ARG(smem <= 200 * 1024, "rfcr: taps / row too large for shared memory (%zu bytes)", smem);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(rfcr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    dim3 grid(op.Ho, op.B);
+    dim3 grid(cdiv(op.Ho, RFCR_ROWS), op.B);
     rfcr_kernel<<<grid, 256, smem, s>>>((const float*)op.in, op.ld_in, K1, (const float*)op.in2, op.ld_in2, K2,
                                         (const float*)op.in3, op.ld_in3, K3, (const float*)op.in4, op.ld_in4, K4, op.w,
                                         op.bias, (float*)op.out, op.ld_out, op.Ho, op.Wo, N);
