@@ -105,21 +105,34 @@ def _dw_ref(x, w, bias, k, s, act):
     (1, 13, 13, 512, 3, 1, "swish"),
     (2, 17, 11, 40, 5, 2, "swish"),
     (1, 5, 3, 8, 3, 1, "none"),
+    (3, 104, 104, 144, 3, 1, "relu6"),  # many spatial tiles per image, last channel tile half empty
+    (3, 104, 104, 144, 3, 2, "relu6"),
+    (2, 208, 208, 24, 3, 1, "relu6"),   # narrow channel box (24 < 32)
+    (5, 52, 52, 128, 3, 1, "swish"),    # more work items than resident CTAs: both pipeline stages wrap
+    (2, 61, 45, 64, 3, 2, "none"),      # odd sizes, ragged tiles in both directions
+    (2, 26, 26, 288, 3, 1, "relu6"),
 ])
-def test_dw_parity(built_lib, B, H, W, C, k, s, act):
+@pytest.mark.parametrize("pad_ld", [0, 24])
+def test_dw_parity(built_lib, B, H, W, C, k, s, act, pad_ld):
+    """pad_ld > 0: input and output are channel slices of wider buffers (the concat layout)."""
     x = _rand(B, H, W, C, seed=1)
     w = _rand(k * k, C, seed=2, scale=0.3)
     bias = _rand(C, seed=3)
     ref, (Ho, Wo, pt, pl) = _dw_ref(x, w, bias, k, s, act)
-    xd, wd, bd = x.cuda(), w.cuda(), bias.cuda()
-    out = torch.full((B, Ho, Wo, C), float("nan"), device="cuda")
+    wd, bd = w.cuda(), bias.cuda()
+    xw = torch.full((B, H, W, C + pad_ld), float("nan"), device="cuda")
+    xw[..., 8 * (pad_ld > 0):8 * (pad_ld > 0) + C] = x.cuda()
+    out = torch.full((B, Ho, Wo, C + pad_ld), float("nan"), device="cuda")
+    off = 8 * (pad_ld > 0)
     op = YrOp()
     op.kind, op.act = _lib.OP_DW, ACT[act]
     op.B, op.H, op.W, op.C, op.Ho, op.Wo, op.N = B, H, W, C, Ho, Wo, C
-    op.k, op.stride, op.pad_t, op.pad_l, op.ld_in, op.ld_out = k, s, pt, pl, C, C
-    op.in_, op.out, op.w, op.bias = xd.data_ptr(), out.data_ptr(), wd.data_ptr(), bd.data_ptr()
+    op.k, op.stride, op.pad_t, op.pad_l, op.ld_in, op.ld_out = k, s, pt, pl, C + pad_ld, C + pad_ld
+    op.in_, op.out, op.w, op.bias = xw.data_ptr() + 4 * off, out.data_ptr() + 4 * off, wd.data_ptr(), bd.data_ptr()
     run_op(op)
-    torch.testing.assert_close(out.cpu().double(), ref, rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(out[..., off:off + C].cpu().double(), ref, rtol=RTOL, atol=ATOL)
+    if pad_ld:
+        assert torch.isnan(out[..., :off]).all() and torch.isnan(out[..., off + C:]).all()
 
 
 @pytest.mark.parametrize("u8", [False, True])

@@ -134,7 +134,10 @@ static void dw_tile(int k, int stride, int& th, int& tw) {
 }
 
 // Number of [C] partial-sum slots per image the fused squeeze-excite sum of this DW op writes.
-int dw_se_slots(const yr_op& op) {
+int dw_se_slots(const yr_op& op_in) {
+    yr_op op = op_in;
+    if (!op.aux) op.aux = reinterpret_cast<float*>(uintptr_t(16));  // "will have a partial-sum buffer": same kernel choice as the launch
+    if (dw_uses_tma(op)) return dw_tma_se_slots(op);
     int th, tw;
     dw_tile(op.k, op.stride, th, tw);
     return cdiv(cdiv(op.Wo, tw) * (op.C / 4), 128) * cdiv(op.Ho, th);
@@ -158,6 +161,7 @@ int launch_dw(const yr_op& op, cudaStream_t s) {
                  "dw: pointers must be 16-byte aligned");
     YR_CHECK_ARG(op.B <= 65535 && cdiv(op.Ho, 1) <= 65535, "dw: grid too large");
     YR_CHECK_ARG(!op.aux || ((uintptr_t)op.aux % 16 == 0 && op.C <= 12288), "dw: bad squeeze-excite partial buffer");
+    if (dw_uses_tma(op)) return launch_dw_tma(op, s);
     switch (op.act) {
         case YR_ACT_NONE: return launch_dw_act<YR_ACT_NONE>(op, s);
         case YR_ACT_RELU6: return launch_dw_act<YR_ACT_RELU6>(op, s);
