@@ -61,6 +61,7 @@ for (H, W, K, N, has_res), names in seen.items():
     tot[3] += n * best[3]
     tot["best"] += n * min(best.values())
     tot["ideal"] += n * ideal
-    print("%3dx%-3d K%-4d N%-4d res%d x%d | v2 %7.1f us | v3 %7.1f us | ideal %6.1f us | v3/v2 %.2f" % (
-        H, W, K, N, has_res, n, best[2], best[3], ideal, best[3] / best[2]), flush=True)
-print("sum over layers (us): v2 %.0f  v3 %.0f  best-of %.0f  ideal(6.5TB/s) %.0f" % (tot[2], tot[3], tot["best"], tot["ideal"]))
+    print("%3dx%-3d K%-4d N%-4d res%d x%d | v2 %7.1f us | v3 %7.1f us | ideal %6.1f us" % (
+        H, W, K, N, has_res, n, best[2], best[3], ideal), flush=True)
+print("sum over layers (us): v2 %.0f  v3 %.0f  best-of %.0f  ideal(6.5TB/s) %.0f" % (
+    tot[2], tot[3], tot["best"], tot["ideal"]))

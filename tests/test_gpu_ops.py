@@ -80,6 +80,23 @@ def test_pw_tensor_core_variants_bit_identical(built_lib, B, H, W, K, N, act, us
     assert torch.equal(o2, o3), float((o2 - o3).abs().max())
 
 
+@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("B,H,W,K,N", [(32, 26, 26, 256, 256), (64, 13, 13, 512, 256), (16, 52, 52, 128, 256)])
+def test_pw_streamed_weights_repeatable(built_lib, variant, B, H, W, K, N):
+    """Wide layers stream their weight tiles through a shared-memory ring while the activation ring, the TMEM
+    stages and the accumulators all wrap many times: 25 back-to-back launches must give the same bits every time
+    (a ring-protocol race shows up as a changed output or a trapped launch, not as a tolerance miss)."""
+    a = _rand(B, H, W, K, seed=21).cuda()
+    w = _rand(K, N, seed=22, scale=K ** -0.5).cuda()
+    bias = _rand(N, seed=23).cuda()
+    first = pw_op(a, w, bias, "relu6", variant=variant)
+    ref = act_ref(a.double().cpu() @ w.double().cpu() + bias.double().cpu(), "relu6")
+    torch.testing.assert_close(first.cpu().double(), ref, rtol=RTOL, atol=ATOL)
+    for _ in range(24):
+        again = pw_op(a, w, bias, "relu6", variant=variant)
+        assert torch.equal(first, again)
+
+
 def _same_pad_lead(size, k, s):
     out = -(-size // s)
     total = max((out - 1) * s + k - size, 0)

@@ -466,7 +466,9 @@ static bool make_tiling(int K, int N, Tiling& t) {
             t.resident = 1;
             t.nB = t.KB;
             long long na = (avail - t.nB * slot - t.nL * tile) / tile;
-            t.nA = (int)(na > MAX_A_STAGES ? MAX_A_STAGES : na);
+            // even ring: each slot then always belongs to the same converter group, which sees every phase of the
+            // slot's mbarrier (an odd ring makes a group skip the phase the other group consumes; see pwconv_ts.cu)
+            t.nA = (int)(na > MAX_A_STAGES ? MAX_A_STAGES : na) & ~1;
             ok = true;
         }
     }
@@ -476,7 +478,7 @@ static bool make_tiling(int K, int N, Tiling& t) {
         t.resident = 0;
         fixed = 1024 + (long long)t.nEpi * EPI_GROUP_BYTES + BAR_BYTES;
         const long long avail = SMEM_LIMIT - fixed;
-        long long nb = (avail - (t.nL + 3) * tile) / slot;  // keep at least 3 raw A slots
+        long long nb = (avail - (t.nL + 4) * tile) / slot;  // keep 4 raw A slots when the weights leave room
         if (nb > 4) nb = 4;
         if (nb > t.KB) nb = t.KB;
         if (nb < 2) nb = 2;
@@ -484,6 +486,7 @@ static bool make_tiling(int K, int N, Tiling& t) {
         if (t.nB >= t.KB && t.n_tiles == 1 && t.KB <= MAX_B_SLOTS) t.resident = 1;
         long long na = (avail - t.nB * slot - t.nL * tile) / tile;
         if (na > MAX_A_STAGES) na = MAX_A_STAGES;
+        na &= ~1ll;
         t.nA = (int)na;
         ok = na >= 2;
     }

@@ -17,8 +17,9 @@
 // memory.  The raw-tile slot is released as soon as the converter has read it, and the (hi, lo) ring
 // costs no shared memory, so more layers keep their whole weight image resident.
 //
-//   warp 0       producer    TMA (SWIZZLE_128B) of 128x32 fp32 A tiles into a ring; bulk copies of the
-//                            pre-split, pre-swizzled weight image (resident when it fits, else a ring)
+//   warp 0       A producer  TMA (SWIZZLE_128B) of 128x32 fp32 A tiles into a ring
+//   warp 18      W producer  bulk copies of the pre-split, pre-swizzled weight image (resident when it fits,
+//                            else a ring of up to 5 slots: the MMA issuer's wait is L2 latency, so depth matters)
 //   warps 2-9    converters  2 groups x 4 warps alternate k-blocks; a thread owns one tile row (= its TMEM
 //                            lane): 8 conflict-free LDS.128, SE gate, hi/lo split, 4 tcgen05.st.x16
 //   warp 1       MMA issuer  3 tcgen05.mma (A in TMEM, B descriptor) per 8-wide K step; tcgen05.commit
@@ -40,7 +41,7 @@ constexpr int BK = 32;
 constexpr int A_TILE_BYTES = BM * BK * 4;
 constexpr int NUM_CONVERTERS = 256;
 constexpr int NUM_EPILOGUE = 256;
-constexpr int NUM_THREADS = 64 + NUM_CONVERTERS + NUM_EPILOGUE;
+constexpr int NUM_THREADS = 64 + NUM_CONVERTERS + NUM_EPILOGUE + 32;  // + A producer, MMA issuer, weight producer warps
 constexpr int EPI_LD = 36;
 constexpr int EPI_STAGE_BYTES = 4 * 32 * EPI_LD * 4;  // per epilogue group: 4 transpose buffers (+ the bias copy)
 constexpr int SMEM_LIMIT = 232448;
@@ -296,32 +297,15 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
     const int item1 = min(item0 + p.items_per_cta, p.total_items);
 
     if (warp == 0) {
-        // ===== producer =====
+        // ===== A producer (the weight slots have their own warp, the last one: a full weight ring never holds
+        // back the activation prefetch and vice versa) =====
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-            Ring ra, rb;
+            Ring ra;
             uint32_t dq = 0;
             int mt = item0 / p.n_tiles, nt = item0 - mt * p.n_tiles;
-            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wp);
-            if (p.resident) {  // the whole weight image, first-needed slots first
-                const int total = p.n_tiles * p.KB;
-                for (int i = 0; i < total; ++i) {
-                    int s = nt * p.KB + i;
-                    if (s >= total) s -= total;
-                    mbar_expect_tx(bar0 + 8u * (BAR_B_FULL + s), b_slot_bytes);
-                    bulk_load(base + b_off + s * b_slot_bytes, wsrc + (size_t)s * b_slot_bytes, b_slot_bytes,
-                              bar0 + 8u * (BAR_B_FULL + s));
-                }
-            }
             for (int item = item0; item < item1; ++item) {
                 for (int kb = 0; kb < p.KB; ++kb) {
-                    if (!p.resident) {
-                        mbar_wait(bar0 + 8u * (BAR_B_EMPTY + rb.slot), rb.phase ^ 1u, 0);
-                        mbar_expect_tx(bar0 + 8u * (BAR_B_FULL + rb.slot), b_slot_bytes);
-                        bulk_load(base + b_off + rb.slot * b_slot_bytes, wsrc + (size_t)(nt * p.KB + kb) * b_slot_bytes,
-                                  b_slot_bytes, bar0 + 8u * (BAR_B_FULL + rb.slot));
-                        rb.advance(p.nB);
-                    }
                     mbar_wait(bar0 + 8u * (BAR_A_EMPTY + ra.slot), ra.phase ^ 1u, 1);
                     mbar_expect_tx(bar0 + 8u * (BAR_A_FULL + ra.slot), A_TILE_BYTES);
                     tma_load_2d(base + a_off + ra.slot * (uint32_t)A_TILE_BYTES, &tmA, bar0 + 8u * (BAR_A_FULL + ra.slot),
@@ -330,6 +314,34 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
                     ra.advance(p.nA);
                 }
                 if (++nt == p.n_tiles) { nt = 0; ++mt; }
+            }
+        }
+    } else if (warp == NUM_THREADS / 32 - 1) {
+        // ===== weight producer =====
+        if (lane == 0) {
+            Ring rb;
+            int nt = item0 % p.n_tiles;
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wp);
+            if (p.resident) {  // the whole weight image once, first-needed slots first
+                const int total = p.n_tiles * p.KB;
+                for (int i = 0; i < total; ++i) {
+                    int s = nt * p.KB + i;
+                    if (s >= total) s -= total;
+                    mbar_expect_tx(bar0 + 8u * (BAR_B_FULL + s), b_slot_bytes);
+                    bulk_load(base + b_off + s * b_slot_bytes, wsrc + (size_t)s * b_slot_bytes, b_slot_bytes,
+                              bar0 + 8u * (BAR_B_FULL + s));
+                }
+            } else {
+                for (int item = item0; item < item1; ++item) {
+                    for (int kb = 0; kb < p.KB; ++kb) {
+                        mbar_wait(bar0 + 8u * (BAR_B_EMPTY + rb.slot), rb.phase ^ 1u, 0);
+                        mbar_expect_tx(bar0 + 8u * (BAR_B_FULL + rb.slot), b_slot_bytes);
+                        bulk_load(base + b_off + rb.slot * b_slot_bytes, wsrc + (size_t)(nt * p.KB + kb) * b_slot_bytes,
+                                  b_slot_bytes, bar0 + 8u * (BAR_B_FULL + rb.slot));
+                        rb.advance(p.nB);
+                    }
+                    if (++nt == p.n_tiles) nt = 0;
+                }
             }
         }
     } else if (warp == 1) {
@@ -383,7 +395,7 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
         const int cw = warp - 2;
         if (p.scale != nullptr) converter_loop<true>(p, gbase + a_off, tmem_base, bar0, item0, item1, warp & 3, lane, cw >> 2);
         else converter_loop<false>(p, gbase + a_off, tmem_base, bar0, item0, item1, warp & 3, lane, cw >> 2);
-    } else {
+    } else if (warp < 2 + (NUM_CONVERTERS + NUM_EPILOGUE) / 32) {
         // ===== epilogue =====
         const int ew8 = warp - (2 + NUM_CONVERTERS / 32);
         const int ew = ew8 & 3, eg = ew8 >> 2;
@@ -459,18 +471,26 @@ static bool make_tiling(int K, int N, Tiling& t) {
     const long long fixed = 1024 + 2ll * t.epi_group_bytes + BAR_BYTES;
     const long long avail = SMEM_LIMIT - fixed;
     const long long wbytes = (long long)t.n_tiles * t.KB * slot;
-    if (t.n_tiles * t.KB <= MAX_B && wbytes + 3 * tile <= avail) {
+    if (t.n_tiles * t.KB <= MAX_B && wbytes + 4 * tile <= avail) {
         t.resident = 1;
         t.nB = t.n_tiles * t.KB;
     } else {
+        // streamed: the MMA issuer waits on weights (L2 latency ~2k cycles against ~800 cycles of MMA per slot), so the
+        // weight ring gets the depth (up to 5 slots) and the raw A ring keeps 4 tiles
         t.resident = 0;
-        long long nb = (avail - 5 * tile) / slot;
-        if (nb > 4) nb = 4;
+        long long nb = (avail - 4 * tile) / slot;
+        if (nb > 5) nb = 5;
+        if (nb > (long long)t.n_tiles * t.KB) nb = (long long)t.n_tiles * t.KB;
         if (nb < 2) nb = 2;
         t.nB = (int)nb;
     }
     long long na = (avail - t.nB * slot) / tile;
     if (na > MAX_A) na = MAX_A;
+    // EVEN ring: the two converter groups alternate k-blocks, so with an even ring every slot belongs to one group
+    // and that group sees each of the slot's mbarrier phases.  With an odd ring a group would skip the phase the
+    // other group consumes, and a 1-bit parity wait cannot tell "two fills ago" from "this fill" when TMA loads
+    // land out of order (observed on B200 with a 3-slot ring: stale tile read, then a protocol deadlock).
+    na &= ~1ll;
     if (na < 2) return false;
     t.nA = (int)na;
     t.smem = (size_t)(fixed + t.nA * tile + t.nB * slot);
@@ -538,12 +558,6 @@ int launch_pw_ts(const yr_op& op, cudaStream_t s) {
     p.a_col0 = t.a_col0;
     p.epi_group_bytes = t.epi_group_bytes;
     p.total_items = p.n_tiles * p.m_tiles;
-    const int sms = tc::num_sms();
-    // whole 128-row blocks per CTA (all n tiles of a block stay on one SM so the A re-read hits L2)
-    const int blocks_per_cta = (p.m_tiles + sms - 1) / sms;
-    p.items_per_cta = blocks_per_cta * p.n_tiles;
-    const int grid = (p.total_items + p.items_per_cta - 1) / p.items_per_cta;
-    p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(t.BN >> 3) << 17) | ((uint32_t)(ts::BM >> 4) << 24);
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(ts::pw_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM_LIMIT) !=
@@ -553,6 +567,12 @@ int launch_pw_ts(const yr_op& op, cudaStream_t s) {
         }
         attr_set = true;
     }
+    const int max_ctas = tc::num_sms();
+    // whole 128-row blocks per CTA (all n tiles of a block stay on one SM so the A re-read hits L2)
+    const int blocks_per_cta = (p.m_tiles + max_ctas - 1) / max_ctas;
+    p.items_per_cta = blocks_per_cta * p.n_tiles;
+    const int grid = (p.m_tiles + blocks_per_cta - 1) / blocks_per_cta;
+    p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(t.BN >> 3) << 17) | ((uint32_t)(ts::BM >> 4) << 24);
     p.dbg = nullptr;
     static const bool debug = getenv("YR_PW_TC_DEBUG") != nullptr;  // developer aid only: timeline of CTA 0
     if (debug) {
@@ -570,8 +590,8 @@ int launch_pw_ts(const yr_op& op, cudaStream_t s) {
         const char* names[8] = {"tma_issue", "a_full_seen", "t_empty_seen", "conv_done", "mma_start", "mma_issued",
                                 "acc_full_seen", "epi_done"};
         long long t0 = h[0];
-        fprintf(stderr, "pw_ts timeline K=%d N=%d BN=%d n_tiles=%d KB=%d nA=%d nT=%d nB=%d nAcc=%d resident=%d items/cta=%d\n",
-                p.K, p.N, p.BN, p.n_tiles, p.KB, p.nA, p.nT, p.nB, p.nAcc, p.resident, p.items_per_cta);
+        fprintf(stderr, "pw_ts timeline K=%d N=%d BN=%d n_tiles=%d KB=%d nA=%d nT=%d nB=%d nAcc=%d resident=%d items/cta=%d grid=%d\n",
+                p.K, p.N, p.BN, p.n_tiles, p.KB, p.nA, p.nT, p.nB, p.nAcc, p.resident, p.items_per_cta, grid);
         for (int r = 0; r < 8; ++r) {
             fprintf(stderr, "%-14s", names[r]);
             for (int i = 0; i < 40 && h[r * ts::DBG_EV + i]; ++i) fprintf(stderr, " %6lld", h[r * ts::DBG_EV + i] - t0);
