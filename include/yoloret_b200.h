@@ -215,6 +215,14 @@ int yr_pack_detections(const float* det, const int32_t* det_count, int B, int nu
 int yr_letterbox_u8(const uint8_t* src, int ih, int iw, float* dst, int h, int w, int nh, int nw, int dy,
                     int dx, void* stream);
 
+/* ---- training input: preprocess_true_boxes (reference code/yolo3/utils.py:298-376) ---
+ * boxes [B][T][5] device f32 (xmin, ymin, xmax, ymax, class) in input pixels, zero-width rows = padding;
+ * anchors: HOST pointer to 9 (w,h) pairs; y_true: HOST array of num_scales DEVICE pointers, each
+ * [B][gh][gw][3][5+num_classes] (gh = round(input_h / {32,16,8}[l])); the tensors are cleared here.
+ * Same slot-collision and row-indexing behaviour as the reference's sequential loop. */
+int yr_encode_true_boxes(const float* boxes, int B, int T, const float* anchors, int input_h, int input_w,
+                         int num_classes, int num_scales, float* const* y_true, void* stream);
+
 /* ---- training: YoloLoss (reference code/yolo3/model.py:585-671) ------------------
  * One scale.  logits / y_true [B,gh,gw,A,5+C] with cell stride ld_logits / ld_true.
  * true_boxes [n_true][4] = tf.boolean_mask(true_box, object_mask) over the WHOLE

@@ -58,3 +58,39 @@ def test_functional_yolo_loss_sums_scales(built_lib, anchors):
     ref = oloss.yolo_loss([y.double() for y in yts], [y.double() for y in yos], anchors)
     got = yolo_loss([y.cuda() for y in yts], [y.cuda() for y in yos], anchors)
     np.testing.assert_allclose(float(got), float(ref), rtol=2e-4)
+
+
+@pytest.mark.parametrize("B,T,hw,ncls,seed", [(4, 8, (416, 416), 80, 0), (3, 20, (320, 480), 20, 1), (5, 6, (96, 96), 4, 2),
+                                              (2, 0, (64, 64), 4, 3)])
+def test_preprocess_true_boxes_gpu_equals_host_and_oracle(built_lib, anchors, B, T, hw, ncls, seed):
+    """The device y_true encoder (yr_encode_true_boxes) == the oracle's restatement of preprocess_true_boxes
+    (reference code/yolo3/utils.py:298-376), bit for bit: float32 floor-divided centres, float64 divisions, best
+    anchor by shape IoU, later boxes overwriting earlier ones in a shared slot (both class bits stay set), zero-width
+    padding rows, and the reference's valid-box counter indexing the unfiltered rows."""
+    from yoloret_b200.yolo3.utils import preprocess_true_boxes_gpu, preprocess_true_boxes
+    rng = np.random.default_rng(seed)
+    boxes = np.zeros((B, T, 5), np.float32)
+    for b in range(B):
+        n = T if b == 0 else int(rng.integers(0, T + 1))        # valid boxes first, zero padding behind (data.py)
+        wh = rng.uniform(4, 0.7 * min(hw), (n, 2))
+        c = rng.uniform(0, 1, (n, 2)) * np.array(hw[::-1])
+        lo = np.clip(np.floor(c - wh / 2), 0, np.array(hw[::-1]) - 2)
+        hi = np.clip(np.ceil(c + wh / 2), lo + 1, np.array(hw[::-1]) - 1)
+        boxes[b, :n, 0:2], boxes[b, :n, 2:4] = lo, hi
+        boxes[b, :n, 4] = rng.integers(0, ncls, n)
+        if n >= 3:                                              # two boxes in one slot, different classes
+            boxes[b, 1] = boxes[b, 0]
+            boxes[b, 1, 4] = (boxes[b, 0, 4] + 1) % ncls
+    if T >= 4:
+        boxes[B - 1, 1, 2] = boxes[B - 1, 1, 0]                 # a zero-width row BEFORE valid ones: the index quirk
+    got = preprocess_true_boxes_gpu(torch.from_numpy(boxes).cuda(), hw, anchors, ncls)
+    torch.cuda.synchronize()
+    for b in range(B):
+        ref = oloss.preprocess_true_boxes(boxes[b], hw, anchors, ncls)
+        host = preprocess_true_boxes(boxes[b], hw, anchors, ncls)
+        for l in range(3):
+            assert got[l].shape[1:] == ref[l].shape
+            assert np.array_equal(host[l], ref[l])
+            assert np.array_equal(got[l][b].cpu().numpy(), ref[l]), (b, l)
+    with pytest.raises(ValueError):
+        preprocess_true_boxes_gpu(torch.from_numpy(boxes), hw, anchors, ncls)   # host tensor: no CPU fallback

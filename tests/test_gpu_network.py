@@ -165,6 +165,34 @@ def test_detect_image_golden(built_lib, tmp_path, variant):
     assert img.size == (500, 375)
 
 
+def test_calculate_map_on_demo_images(built_lib, tmp_path):
+    """The mAP harness (reference code/yolo.py:397-405, code/yolo3/map.py) end to end on the GPU engine: the 7 demo
+    JPEGs with the committed golden detections as ground truth (VOC text-list format).  Every golden box is found
+    again as the top-scoring match of its class, so each class that occurs has AP 1 and the others AP 0."""
+    from yoloret_b200.yolo3.map import calculate_map
+    g = np.load(os.path.join(GOLD, "demo_golden.npz"))
+    (tmp_path / "anchors.txt").write_text(",  ".join("%g,%g" % (a, b) for a, b in g["anchors"]))
+    classes = ["aeroplane", "bicycle", "bird", "boat", "bottle", "bus", "car", "cat", "chair", "cow", "diningtable",
+               "dog", "horse", "motorbike", "person", "pottedplant", "sheep", "sofa", "train", "tvmonitor"]
+    (tmp_path / "classes.txt").write_text("\n".join(classes) + "\n")
+    lines, present = [], set()
+    for i in range(len(g["names"])):
+        (tmp_path / ("img%d.jpg" % i)).write_bytes(g["jpeg_%d" % i].tobytes())
+        parts = ["img%d.jpg" % i]
+        for (top, left, bottom, right), c in zip(g["det_boxes_i_%d" % i], g["det_classes_%d" % i]):
+            parts += [str(int(left)), str(int(top)), str(int(right)), str(int(bottom)), str(int(c))]
+            present.add(int(c))
+        lines.append(" ".join(parts))
+    (tmp_path / "list.txt").write_text("\n".join(lines) + "\n")
+    yolo = YOLO({"backbone": BACKBONE.MOBILENETV2x75, "classes_path": str(tmp_path / "classes.txt"),
+                 "anchors_path": str(tmp_path / "anchors.txt"), "input_size": (320, 320), "score": 0.3, "nms": 0.5,
+                 "weights": _golden_weights(), "model": "golden", "quiet": True})
+    mAP, aps = calculate_map(yolo, str(tmp_path / "list.txt"), image_root=str(tmp_path))
+    for c in range(20):
+        assert aps[c] == pytest.approx(1.0 if c in present else 0.0), (c, aps[c])
+    assert mAP == pytest.approx(len(present) / 20.0)
+
+
 def test_detect_batch_graph_equals_eager(built_lib, anchors, tmp_path):
     hw, ncls, B = (96, 96), 20, 4
     nd = NetDef("mobilenetv2x75", ncls, hw)

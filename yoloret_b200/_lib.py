@@ -81,6 +81,8 @@ SYMBOLS = {
     "yr_yolo_loss_workspace": (C.c_int64, [C.POINTER(YrLossParams)]),
     "yr_yolo_loss_gather_true": (C.c_int, [_P, C.POINTER(YrLossParams), _P, _P, _P]),
     "yr_yolo_loss": (C.c_int, [_P, _P, _P, _P, C.POINTER(YrLossParams), _P, _P, _P, C.c_int64, _P]),
+    "yr_encode_true_boxes": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.POINTER(_P), _P]),
 }
 
 

@@ -617,46 +617,76 @@ int launch_se(const yr_op& op, cudaStream_t s) {
 // (dwconv.cu): the global mean never re-reads the activation.  One CTA per image.
 //   w = [w1t R x F | w2 R x F],  bias = [b1 R | b2 F]   (w1 TRANSPOSED so a warp reads it coalesced)
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-se_fc_kernel(const float* __restrict__ part, int slots, int HW, int F, int R, const float* __restrict__ w1t,
+// One CTA serves SE_IPC images, so every weight row fetched from L2 feeds SE_IPC dot products (a CTA per image had
+// 256 CTAs pulling the same 0.5 MB of weights through the same L2 slices at the same time: 58 us for F = 512).
+// Per image the arithmetic and its order are those of a CTA-per-image kernel: lane-strided partial sums + xor-shuffle
+// tree for the first FC, a sequential fmaf chain over r for the second, so the gate of an image does not depend on its
+// position in the batch.
+constexpr int SE_IPC = 4;
+
+__global__ void __launch_bounds__(512)
+se_fc_kernel(const float* __restrict__ part, int slots, int HW, int F, int R, int B, const float* __restrict__ w1t,
              const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
              float* __restrict__ gate) {
     extern __shared__ __align__(16) float sm[];
-    float* mean = sm;      // [F]
-    float* hid = sm + F;   // [R]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float* pb = part + (size_t)blockIdx.x * slots * F;
-    for (int f4 = tid; f4 < (F >> 2); f4 += 256) {
+    float* mean = sm;                 // [SE_IPC][F]
+    float* hid = sm + SE_IPC * F;     // [SE_IPC][R]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int img0 = blockIdx.x * SE_IPC;
+    const int F4 = F >> 2;
+    for (int i = tid; i < SE_IPC * F4; i += blockDim.x) {
+        const int im = i / F4, f4 = i - im * F4;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int sl = 0; sl < slots; ++sl) {  // fixed order: deterministic
-            const float4 v = ldg4(pb + (size_t)sl * F + f4 * 4);
-            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        if (img0 + im < B) {
+            const float* pb = part + (size_t)(img0 + im) * slots * F;
+            for (int sl = 0; sl < slots; ++sl) {  // fixed order: deterministic
+                const float4 v = ldg4(pb + (size_t)sl * F + f4 * 4);
+                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            }
         }
         const float d = (float)HW;
-        st4(mean + f4 * 4, make_float4(a.x / d, a.y / d, a.z / d, a.w / d));
+        st4(mean + im * F + f4 * 4, make_float4(a.x / d, a.y / d, a.z / d, a.w / d));
     }
     __syncthreads();
-    for (int r = warp; r < R; r += 8) {
-        float a = 0.f;
-        for (int f = lane; f < F; f += 32) a = fmaf(mean[f], __ldg(w1t + (size_t)r * F + f), a);
+    for (int r = warp; r < R; r += nwarps) {
+        float a[SE_IPC];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        for (int im = 0; im < SE_IPC; ++im) a[im] = 0.f;
+#pragma unroll 8   // 8 independent weight loads in flight per lane: the loop is L2-latency bound otherwise
+        for (int f = lane; f < F; f += 32) {
+            const float w = __ldg(w1t + (size_t)r * F + f);
+#pragma unroll
+            for (int im = 0; im < SE_IPC; ++im) a[im] = fmaf(mean[im * F + f], w, a[im]);
+        }
+#pragma unroll
+        for (int im = 0; im < SE_IPC; ++im) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a[im] += __shfl_xor_sync(0xffffffffu, a[im], o);
+        }
         if (lane == 0) {
-            a += __ldg(b1 + r);
-            hid[r] = a * (1.0f / (1.0f + expf(-a)));
+            const float bb = __ldg(b1 + r);
+#pragma unroll
+            for (int im = 0; im < SE_IPC; ++im) {
+                const float v = a[im] + bb;
+                hid[im * R + r] = v * (1.0f / (1.0f + expf(-v)));
+            }
         }
     }
     __syncthreads();
-    // second FC: this CTA's slice of the F outputs (gridDim.y CTAs per image share the work; the squeeze
-    // and the first FC above are recomputed per slice - they are tiny, the weight read of FC2 is not)
-    const int per = (F + gridDim.y - 1) / gridDim.y;
-    const int f_end = min(F, (int)(blockIdx.y + 1) * per);
-    for (int f = blockIdx.y * per + tid; f < f_end; f += 256) {
-        float a = 0.f;
+    for (int f = tid; f < F; f += blockDim.x) {
+        float a[SE_IPC];
+#pragma unroll
+        for (int im = 0; im < SE_IPC; ++im) a[im] = 0.f;
 #pragma unroll 8
-        for (int r = 0; r < R; ++r) a = fmaf(hid[r], __ldg(w2 + (size_t)r * F + f), a);
-        a += __ldg(b2 + f);
-        gate[(size_t)blockIdx.x * F + f] = 1.0f / (1.0f + expf(-a));
+        for (int r = 0; r < R; ++r) {
+            const float w = __ldg(w2 + (size_t)r * F + f);
+#pragma unroll
+            for (int im = 0; im < SE_IPC; ++im) a[im] = fmaf(hid[im * R + r], w, a[im]);
+        }
+        const float bb = __ldg(b2 + f);
+#pragma unroll
+        for (int im = 0; im < SE_IPC; ++im)
+            if (img0 + im < B) gate[(size_t)(img0 + im) * F + f] = 1.0f / (1.0f + expf(-(a[im] + bb)));
     }
 }
 
@@ -664,12 +694,10 @@ int launch_se_fc(const yr_op& op, cudaStream_t s) {
     YR_CHECK_ARG(op.in && op.out && op.w && op.bias, "se_fc: null pointer");
     const int F = op.C, R = op.N, slots = op.K2;
     YR_CHECK_ARG(F % 4 == 0 && R > 0 && slots > 0 && op.H > 0 && op.W > 0, "se_fc: unsupported F=%d R=%d slots=%d", F, R, slots);
-    const size_t smem = (size_t)(F + R) * sizeof(float);
+    const size_t smem = (size_t)SE_IPC * (F + R) * sizeof(float);
     YR_CHECK_ARG(smem <= 48 * 1024, "se_fc: F too large");
-    YR_CHECK_ARG(op.B <= 65535, "se_fc: batch too large");
-    dim3 grid(op.B, F >= 256 ? 4 : (F >= 128 ? 2 : 1));
-    se_fc_kernel<<<grid, 256, smem, s>>>((const float*)op.in, slots, op.H * op.W, F, R, op.w, op.bias,
-                                         op.w + (size_t)F * R, op.bias + R, (float*)op.out);
+    se_fc_kernel<<<cdiv(op.B, SE_IPC), 512, smem, s>>>((const float*)op.in, slots, op.H * op.W, F, R, op.B, op.w, op.bias,
+                                                        op.w + (size_t)F * R, op.bias + R, (float*)op.out);
     YR_CHECK_LAUNCH("se_fc");
     return YR_OK;
 }

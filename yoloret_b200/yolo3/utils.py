@@ -93,3 +93,26 @@ def encode_true_boxes_batch(boxes_batch, input_shape, anchors, num_classes, num_
     """Stacks ``preprocess_true_boxes`` over a batch: list of [T,5] -> list (per scale) of [B,gh,gw,3,5+C]."""
     per_image = [preprocess_true_boxes(b, input_shape, anchors, num_classes, num_scales) for b in boxes_batch]
     return [np.stack([y[l] for y in per_image]) for l in range(num_scales)]
+
+
+def preprocess_true_boxes_gpu(true_boxes: torch.Tensor, input_shape, anchors, num_classes, num_scales=3):
+    """``preprocess_true_boxes`` for a whole batch on the GPU (reference code/yolo3/utils.py:298-376, which the
+    reference runs per sample as a numpy py_function, code/yolo3/data.py:84-121).  ``true_boxes``: float32 CUDA
+    tensor [B,T,5] = (xmin, ymin, xmax, ymax, class) in input pixels, zero-width rows are padding.  Returns the
+    per-scale dense y_true tensors [B,gh,gw,3,5+num_classes] (CUDA), bit-identical to stacking the host encoder."""
+    if not (true_boxes.is_cuda and true_boxes.dtype == torch.float32 and true_boxes.dim() == 3 and true_boxes.shape[2] == 5):
+        raise ValueError("preprocess_true_boxes_gpu expects a float32 CUDA tensor [B,T,5]")
+    import ctypes as C
+    tb = true_boxes.contiguous()
+    B, T = int(tb.shape[0]), int(tb.shape[1])
+    h, w = int(input_shape[0]), int(input_shape[1])
+    anc = np.ascontiguousarray(np.asarray(anchors, np.float32).reshape(-1))
+    if anc.size != 18:
+        raise ValueError("preprocess_true_boxes needs the 9 anchors (18 numbers), got %d" % anc.size)
+    grids = [np.round(np.array([h, w], np.int32) / s).astype(np.int32) for s in (32, 16, 8)[:num_scales]]
+    ys = [torch.empty(B, int(g[0]), int(g[1]), 3, 5 + num_classes, dtype=torch.float32, device=tb.device) for g in grids]
+    ptrs = (C.c_void_p * num_scales)(*[y.data_ptr() for y in ys])
+    st = torch.cuda.current_stream(tb.device).cuda_stream
+    _lib.check(_lib.lib().yr_encode_true_boxes(tb.data_ptr(), B, T, anc.ctypes.data_as(C.POINTER(C.c_float)), h, w,
+                                               num_classes, num_scales, ptrs, st), "yr_encode_true_boxes")
+    return ys
