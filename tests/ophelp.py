@@ -25,15 +25,16 @@ def act_ref(x, act):
     return x
 
 
-def pw_op(a, w, bias, act="none", res=None, scale=None, ld_out=None, variant=0):
-    """a [B,H,W,ld_in] (uses first K=w.shape[0] channels), w [K,N], returns [B,H,W,N]."""
+def pw_op(a, w, bias, act="none", res=None, scale=None, ld_out=None, variant=0, up2=False):
+    """a [B,H,W,ld_in] (uses first K=w.shape[0] channels), w [K,N], returns [B,H,W,N] ([B,2H,2W,N] with up2)."""
     B, H, W, ld = a.shape
     K, N = w.shape
     ldo = ld_out or N
-    out = torch.full((B, H, W, ldo), float("nan"), device="cuda")
+    Ho, Wo = (2 * H, 2 * W) if up2 else (H, W)
+    out = torch.full((B, Ho, Wo, ldo), float("nan"), device="cuda")
     op = YrOp()
     op.kind, op.act, op.variant = _lib.OP_PW, ACT[act], variant
-    op.B, op.H, op.W, op.C, op.Ho, op.Wo, op.N = B, H, W, K, H, W, N
+    op.B, op.H, op.W, op.C, op.Ho, op.Wo, op.N = B, H, W, K, Ho, Wo, N
     op.ld_in, op.ld_out = ld, ldo
     op.in_, op.out, op.w, op.bias = a.data_ptr(), out.data_ptr(), w.data_ptr(), bias.data_ptr()
     if res is not None:

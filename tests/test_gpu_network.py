@@ -78,6 +78,23 @@ def test_fused_blocks_equal_unfused(built_lib, anchors):
         assert torch.equal(a, b), float((a - b).abs().max())
 
 
+def test_fused_upsampling_equals_separate_resample(built_lib, anchors):
+    """The engine folds UpSampling2D into the producing 1x1 conv's epilogue (block_20_conv / block_24_conv): logits
+    bit-identical to running the resample op on its own, with fewer launches."""
+    hw, ncls, B = (128, 160), 80, 3
+    nd = NetDef("mobilenetv2x75", ncls, hw)
+    w = synthetic_weights(nd.weight_shapes, ncls, seed=29)
+    x = torch.rand(B, hw[0], hw[1], 3, generator=torch.Generator().manual_seed(6)).cuda()
+    mf = yolov3_body((B, hw[0], hw[1], 3), "mobilenetv2x75", 3, num_classes=ncls, fuse_up2=True).set_weights(w, anchors)
+    mu = yolov3_body((B, hw[0], hw[1], 3), "mobilenetv2x75", 3, num_classes=ncls, fuse_up2=False).set_weights(w, anchors)
+    yf = [y.clone() for y in mf(x)]
+    yu = [y.clone() for y in mu(x)]
+    for a, b in zip(yf, yu):
+        assert torch.equal(a, b), float((a - b).abs().max())
+    nf, nu = mf.engine.build_plan(0, B)[1], mu.engine.build_plan(0, B)[1]
+    assert nf == nu - 2, (nf, nu)
+
+
 @pytest.mark.parametrize("lanes,micro", [(2, None), (3, 2), (4, None)])
 def test_lanes_equal_single_stream(built_lib, anchors, lanes, micro):
     """Concurrent micro-batch lanes (fork/join over CUDA streams, one arena per lane) change nothing in the

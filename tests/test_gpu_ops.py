@@ -81,6 +81,24 @@ def test_pw_tensor_core_variants_bit_identical(built_lib, B, H, W, K, N, act, us
 
 
 @pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("B,H,W,K,N,act", [(3, 13, 13, 256, 256, "relu6"), (2, 26, 26, 256, 128, "relu6"), (2, 7, 5, 48, 48, "swish"),
+                                           (5, 26, 26, 48, 96, "none")])
+def test_pw_fused_upsampling(built_lib, variant, B, H, W, K, N, act):
+    """Conv1x1+BN+act followed by UpSampling2D (nearest x2, reference code/yolo3/model.py:254,274) as ONE op: the
+    epilogue stores every output row to its 2x2 upsampled pixels of a wider concat buffer.  Must equal the plain op
+    followed by a nearest upsample bit for bit, and leave the rest of the buffer alone."""
+    a = _rand(B, H, W, K, seed=31).cuda()
+    w = _rand(K, N, seed=32, scale=K ** -0.5).cuda()
+    bias = _rand(N, seed=33).cuda()
+    plain = pw_op(a, w, bias, act, variant=variant)
+    fused = pw_op(a, w, bias, act, variant=variant, ld_out=N + 16, up2=True)
+    want = plain.repeat_interleave(2, 1).repeat_interleave(2, 2)
+    assert fused.shape == (B, 2 * H, 2 * W, N + 16)
+    assert torch.equal(fused[..., :N], want)
+    assert torch.isnan(fused[..., N:]).all()
+
+
+@pytest.mark.parametrize("variant", [2, 3])
 @pytest.mark.parametrize("B,H,W,K,N", [(32, 26, 26, 256, 256), (64, 13, 13, 512, 256), (16, 52, 52, 128, 256)])
 def test_pw_streamed_weights_repeatable(built_lib, variant, B, H, W, K, N):
     """Wide layers stream their weight tiles through a shared-memory ring while the activation ring, the TMEM

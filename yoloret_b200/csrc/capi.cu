@@ -1,10 +1,19 @@
 // C-ABI glue: error state, plan executor, letterbox pre-process.
 #include "yr_common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace yr {
 
 static thread_local char g_err[512] = "";
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("YR_PDL");
+        return e != nullptr && atoi(e) != 0;  // opt-in: measured on B200, no gain inside the captured graph
+    }();
+    return on;
+}
 
 void set_error(const char* fmt, ...) {
     va_list ap;

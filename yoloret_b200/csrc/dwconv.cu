@@ -21,6 +21,8 @@ dw_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ wgt
     constexpr int IN_ROWS = (TH - 1) * S + KS;
     constexpr int IN_COLS = (TW - 1) * S + KS;
     extern __shared__ __align__(16) float s_sum[];  // [C], only when part != nullptr
+    pdl_wait();
+    pdl_launch_dependents();
     const int C4 = C >> 2;
     const int wtiles = (Wo + TW - 1) / TW;
     const int item = blockIdx.x * 128 + threadIdx.x;
@@ -121,10 +123,11 @@ static int launch_dw_cfg(const yr_op& op, cudaStream_t s) {
     const int items = cdiv(op.Wo, TW) * (op.C / 4);
     dim3 grid(cdiv(items, 128), cdiv(op.Ho, TH), op.B);
     const size_t smem = op.aux ? (size_t)op.C * sizeof(float) : 0;
-    dw_kernel<KS, S, TH, TW, ACT><<<grid, 128, smem, s>>>((const float*)op.in, op.ld_in, op.w, op.bias, (float*)op.out,
-                                                           op.ld_out, op.H, op.W, op.C, op.Ho, op.Wo, op.pad_t, op.pad_l,
-                                                           op.aux);
-    YR_CHECK_LAUNCH("dw");
+    if (launch_pdl(dw_kernel<KS, S, TH, TW, ACT>, grid, dim3(128), smem, s, (const float*)op.in, op.ld_in, op.w, op.bias,
+                   (float*)op.out, op.ld_out, op.H, op.W, op.C, op.Ho, op.Wo, op.pad_t, op.pad_l, op.aux) != cudaSuccess) {
+        set_error("dw: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return YR_ERR_CUDA;
+    }
     return YR_OK;
 }
 

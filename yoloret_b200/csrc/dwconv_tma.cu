@@ -65,6 +65,8 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tm, const Params p) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm) : "memory");
     }
     __syncthreads();
+    pdl_wait();  // programmatic dependent launch: the input is the previous kernel's output
+    pdl_launch_dependents();
 
     const uint32_t stage_bytes = (uint32_t)p.stage_floats * 4u;
     const uint32_t box_bytes = (uint32_t)p.IH * p.IW * p.cb * 4u;
@@ -294,8 +296,10 @@ static int launch_dw_tma_cfg(const yr_op& op, const dwt::Plan& pl, const CUtenso
         if (smem * n + 4096 * n <= 227 * 1024 && pl.threads * n <= 2048 && pl.threads * n * 128 <= 65536) per_sm = n;
     int grid = sms * per_sm;
     if (grid > p.total) grid = p.total;
-    dwt::dw_tma_kernel<S, ACT><<<grid, pl.threads, smem, s>>>(tm, p);
-    YR_CHECK_LAUNCH("dw_tma");
+    if (launch_pdl(dwt::dw_tma_kernel<S, ACT>, dim3(grid), dim3(pl.threads), smem, s, tm, p) != cudaSuccess) {
+        set_error("dw_tma: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return YR_ERR_CUDA;
+    }
     return YR_OK;
 }
 

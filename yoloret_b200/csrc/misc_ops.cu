@@ -137,6 +137,8 @@ stem_kernel_v3(const void* __restrict__ in_, const float* __restrict__ wgt, cons
                float* __restrict__ out, int ld_out, int H, int W, int Ho, int Wo, int N, int pad_t, int pad_l, int TH,
                int row_floats) {
     extern __shared__ __align__(16) float sm3[];
+    pdl_wait();
+    pdl_launch_dependents();
     float* sw = sm3;                       // [27][N]
     float* sx = sm3 + ((27 * N + 3) & ~3);  // [2*TH+1][row_floats]: pad_l zero pixels, the row, zero tail
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -285,8 +287,8 @@ static bool launch_stem_v3(const yr_op& op, cudaStream_t s) {
         attr_set = true;
     }
     dim3 grid(cdiv(op.Ho, TH), op.B);
-    stem_kernel_v3<ACT, U8, CPT><<<grid, threads, smem, s>>>(op.in, op.w, op.bias, (float*)op.out, op.ld_out, op.H, op.W,
-                                                              op.Ho, op.Wo, op.N, op.pad_t, op.pad_l, TH, row_floats);
+    launch_pdl(stem_kernel_v3<ACT, U8, CPT>, grid, dim3(threads), smem, s, op.in, op.w, op.bias, (float*)op.out, op.ld_out,
+               op.H, op.W, op.Ho, op.Wo, op.N, op.pad_t, op.pad_l, TH, row_floats);
     return true;
 }
 
@@ -347,6 +349,8 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 resample_kernel(const float* __restrict__ in, int ld_in, float* __restrict__ out, int ld_out, int B, int H, int W,
                 int C, int Ho, int Wo) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int C4 = C >> 2;
     const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (item >= (long long)B * Ho * Wo * C4) return;
@@ -380,13 +384,13 @@ int launch_resample(const yr_op& op, cudaStream_t s) {
     float* out = (float*)op.out;
     if (op.mode == YR_UP2) {
         YR_CHECK_ARG(op.Ho == op.H * 2 && op.Wo == op.W * 2, "resample up2: bad output size");
-        resample_kernel<YR_UP2><<<grid, 256, 0, s>>>(in, op.ld_in, out, op.ld_out, op.B, op.H, op.W, op.C, op.Ho, op.Wo);
+        launch_pdl(resample_kernel<YR_UP2>, dim3(grid), dim3(256), 0, s, in, op.ld_in, out, op.ld_out, op.B, op.H, op.W, op.C, op.Ho, op.Wo);
     } else if (op.mode == YR_POOL2) {
         YR_CHECK_ARG(op.Ho == op.H / 2 && op.Wo == op.W / 2, "resample pool2: bad output size");
-        resample_kernel<YR_POOL2><<<grid, 256, 0, s>>>(in, op.ld_in, out, op.ld_out, op.B, op.H, op.W, op.C, op.Ho, op.Wo);
+        launch_pdl(resample_kernel<YR_POOL2>, dim3(grid), dim3(256), 0, s, in, op.ld_in, out, op.ld_out, op.B, op.H, op.W, op.C, op.Ho, op.Wo);
     } else if (op.mode == YR_POOL4) {
         YR_CHECK_ARG(op.Ho == op.H / 4 && op.Wo == op.W / 4, "resample pool4: bad output size");
-        resample_kernel<YR_POOL4><<<grid, 256, 0, s>>>(in, op.ld_in, out, op.ld_out, op.B, op.H, op.W, op.C, op.Ho, op.Wo);
+        launch_pdl(resample_kernel<YR_POOL4>, dim3(grid), dim3(256), 0, s, in, op.ld_in, out, op.ld_out, op.B, op.H, op.W, op.C, op.Ho, op.Wo);
     } else {
         set_error("resample: unknown mode %d", op.mode);
         return YR_ERR_INVALID;
@@ -426,6 +430,8 @@ rfcr_kernel(const float* __restrict__ b1, int ld1, int K1, const float* __restri
             const float* __restrict__ wgt, const float* __restrict__ alpha, float* __restrict__ out, int ld_out, int H,
             int W, int N) {
     extern __shared__ __align__(16) float sm[];
+    pdl_wait();
+    pdl_launch_dependents();
     const int KT = K1 + K2 + K3 + K4;
     const int W1 = W >> 1, H1 = H >> 1;
     float* sw = sm;                     // [KT][N]
@@ -543,9 +549,9 @@ int launch_rfcr(const yr_op& op, cudaStream_t s) {
         attr_set = true;
     }
     dim3 grid(cdiv(op.Ho, RFCR_ROWS), op.B);
-    rfcr_kernel<<<grid, 256, smem, s>>>((const float*)op.in, op.ld_in, K1, (const float*)op.in2, op.ld_in2, K2,
-                                        (const float*)op.in3, op.ld_in3, K3, (const float*)op.in4, op.ld_in4, K4, op.w,
-                                        op.bias, (float*)op.out, op.ld_out, op.Ho, op.Wo, N);
+    launch_pdl(rfcr_kernel, grid, dim3(256), smem, s, (const float*)op.in, op.ld_in, K1, (const float*)op.in2, op.ld_in2, K2,
+               (const float*)op.in3, op.ld_in3, K3, (const float*)op.in4, op.ld_in4, K4, op.w, op.bias, (float*)op.out,
+               op.ld_out, op.Ho, op.Wo, N);
     YR_CHECK_LAUNCH("rfcr");
     return YR_OK;
 }
@@ -629,6 +635,8 @@ se_fc_kernel(const float* __restrict__ part, int slots, int HW, int F, int R, in
              const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
              float* __restrict__ gate) {
     extern __shared__ __align__(16) float sm[];
+    pdl_wait();
+    pdl_launch_dependents();
     float* mean = sm;                 // [SE_IPC][F]
     float* hid = sm + SE_IPC * F;     // [SE_IPC][R]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -696,8 +704,8 @@ int launch_se_fc(const yr_op& op, cudaStream_t s) {
     YR_CHECK_ARG(F % 4 == 0 && R > 0 && slots > 0 && op.H > 0 && op.W > 0, "se_fc: unsupported F=%d R=%d slots=%d", F, R, slots);
     const size_t smem = (size_t)SE_IPC * (F + R) * sizeof(float);
     YR_CHECK_ARG(smem <= 48 * 1024, "se_fc: F too large");
-    se_fc_kernel<<<cdiv(op.B, SE_IPC), 512, smem, s>>>((const float*)op.in, slots, op.H * op.W, F, R, op.B, op.w, op.bias,
-                                                        op.w + (size_t)F * R, op.bias + R, (float*)op.out);
+    launch_pdl(se_fc_kernel, dim3(cdiv(op.B, SE_IPC)), dim3(512), smem, s, (const float*)op.in, slots, op.H * op.W, F, R, op.B,
+               op.w, op.bias, op.w + (size_t)F * R, op.bias + R, (float*)op.out);
     YR_CHECK_LAUNCH("se_fc");
     return YR_OK;
 }

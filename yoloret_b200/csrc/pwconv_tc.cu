@@ -47,6 +47,7 @@ struct Params {
     float* out;
     int M, K, N, BN, n_tiles, m_tiles, KB;
     int ld_out, ld_res, rows_per_img, act;
+    int up2, img_w;  // up2: every output row is stored to its 2x2 nearest-upsampled pixels (fused UpSampling2D)
     int nA, nL, nB, nAcc, nEpi, resident, tmem_cols, acc_stride, items_per_cta, total_items;
     uint32_t idesc;
     long long* dbg;  // optional timeline of CTA 0 (YR_PW_TC_DEBUG=1), else NULL
@@ -81,7 +82,7 @@ __device__ __forceinline__ int group_size(const Params& p, int item, int item1, 
 // One warp owns TMEM lane quarter q (32 tile rows).  Per 32-column chunk: the accumulator row a lane
 // holds goes to smem as 8 STS.128 (row stride 36 floats: conflict-free per 8-lane phase), comes back
 // as LDS.128 with 8 lanes covering one row, and leaves as STG.128: 4 full 128-byte lines per store.
-template <int ACT, bool HAS_RES>
+template <int ACT, bool HAS_RES, bool UP2>
 __device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, float* s_bias, uint32_t tmem_base,
                                               uint32_t bar0, int item0, int item1, int q, int lane, int ewarp, int grp) {
     const int sub_r = lane >> 3;        // row within a 4-row group
@@ -150,7 +151,21 @@ __device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, float
                         x.z = apply_act<ACT>(x.z + bv.z);
                         x.w = apply_act<ACT>(x.w + bv.w);
                         if (HAS_RES) { x.x += rv[i].x; x.y += rv[i].y; x.z += rv[i].z; x.w += rv[i].w; }
-                        st4(op + (size_t)i * ostep, x);
+                        if (!UP2) {
+                            st4(op + (size_t)i * ostep, x);
+                        } else {
+                            // fused UpSampling2D (nearest x2, reference code/yolo3/model.py:254,274): input pixel
+                            // (b, h, w) -> output pixels (2h..2h+1, 2w..2w+1) of the [B, 2H, 2W, ld_out] tensor
+                            const int m = row0 + sub_r + 4 * i;
+                            const int bi = m / p.rows_per_img, rem = m - bi * p.rows_per_img;
+                            const int h = rem / p.img_w, w = rem - h * p.img_w;
+                            const size_t wo2 = (size_t)2 * p.img_w;
+                            float* d = p.out + (((size_t)bi * 2 * (p.rows_per_img / p.img_w) + 2 * h) * wo2 + 2 * w) * p.ld_out + n;
+                            st4(d, x);
+                            st4(d + p.ld_out, x);
+                            st4(d + wo2 * p.ld_out, x);
+                            st4(d + (wo2 + 1) * p.ld_out, x);
+                        }
                     }
                 }
             }
@@ -278,6 +293,11 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
     const int item0 = blockIdx.x * p.items_per_cta;
     const int item1 = min(item0 + p.items_per_cta, p.total_items);
 
+    // programmatic dependent launch: the prologue above overlapped the previous kernel's tail; from here on the
+    // kernel reads what that kernel wrote
+    pdl_wait();
+    pdl_launch_dependents();
+
     if (warp == 0) {
         // ===== producer =====
         if (lane == 0) {
@@ -389,16 +409,19 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
         const bool has_res = p.res != nullptr;
         switch (p.act) {
             case YR_ACT_RELU6:
-                if (has_res) epilogue_loop<YR_ACT_RELU6, true>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                else epilogue_loop<YR_ACT_RELU6, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                if (has_res) epilogue_loop<YR_ACT_RELU6, true, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else if (p.up2) epilogue_loop<YR_ACT_RELU6, false, true>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else epilogue_loop<YR_ACT_RELU6, false, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
                 break;
             case YR_ACT_SWISH:
-                if (has_res) epilogue_loop<YR_ACT_SWISH, true>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                else epilogue_loop<YR_ACT_SWISH, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                if (has_res) epilogue_loop<YR_ACT_SWISH, true, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else if (p.up2) epilogue_loop<YR_ACT_SWISH, false, true>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else epilogue_loop<YR_ACT_SWISH, false, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
                 break;
             default:
-                if (has_res) epilogue_loop<YR_ACT_NONE, true>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                else epilogue_loop<YR_ACT_NONE, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                if (has_res) epilogue_loop<YR_ACT_NONE, true, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else if (p.up2) epilogue_loop<YR_ACT_NONE, false, true>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else epilogue_loop<YR_ACT_NONE, false, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
         }
         }
     }
@@ -516,6 +539,9 @@ int launch_pw_tc(const yr_op& op, cudaStream_t s) {
                   (uintptr_t)op.scale) % 16 == 0, "pw_tc: pointers must be 16-byte aligned");
     const long long M = (long long)op.B * op.H * op.W;
     YR_CHECK_ARG(M > 0 && M < (1ll << 31) - 256, "pw_tc: bad row count");
+    YR_CHECK_ARG((op.Ho == op.H && op.Wo == op.W) || (op.Ho == 2 * op.H && op.Wo == 2 * op.W && !op.res),
+                 "pw_tc: output must be HxW, or 2Hx2W (fused nearest upsampling, no residual): got %dx%d for %dx%d", op.Ho, op.Wo,
+                 op.H, op.W);
     tc::Tiling t;
     if (!tc::make_tiling(op.C, op.N, t)) {
         set_error("pw_tc: no tiling for K=%d N=%d", op.C, op.N);
@@ -554,6 +580,8 @@ int launch_pw_tc(const yr_op& op, cudaStream_t s) {
     p.ld_out = op.ld_out;
     p.ld_res = op.ld_res;
     p.rows_per_img = op.H * op.W;
+    p.img_w = op.W;
+    p.up2 = (op.Ho == 2 * op.H && op.Wo == 2 * op.W) ? 1 : 0;
     p.act = op.act;
     p.nA = t.nA;
     p.nL = t.nL;
@@ -586,8 +614,10 @@ int launch_pw_tc(const yr_op& op, cudaStream_t s) {
         cudaMemsetAsync(dbuf, 0, 8 * tc::DBG_EV * sizeof(long long), s);
         p.dbg = dbuf;
     }
-    tc::pw_tc_kernel<<<grid, tc::NUM_THREADS, t.smem, s>>>(tm, p);
-    YR_CHECK_LAUNCH("pw_tc");
+    if (launch_pdl(tc::pw_tc_kernel, dim3(grid), dim3(tc::NUM_THREADS), t.smem, s, tm, p) != cudaSuccess) {
+        set_error("pw_tc: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return YR_ERR_CUDA;
+    }
     if (debug) {
         static long long h[8 * tc::DBG_EV];
         cudaStreamSynchronize(s);

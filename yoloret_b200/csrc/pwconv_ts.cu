@@ -57,6 +57,7 @@ struct Params {
     float* out;
     int M, K, N, BN, n_tiles, m_tiles, KB;
     int ld_out, ld_res, rows_per_img, act;
+    int up2, img_w;  // up2: every output row is stored to its 2x2 nearest-upsampled pixels (fused UpSampling2D)
     int nA, nT, nB, nAcc, resident, acc_stride, a_col0, items_per_cta, total_items, epi_group_bytes;
     uint32_t idesc;
     long long* dbg;
@@ -101,7 +102,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- epilogue (see pwconv_tc.cu for the access pattern; items here are m-major) ---------------
-template <int ACT, bool HAS_RES>
+template <int ACT, bool HAS_RES, bool UP2>
 __device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, const float* s_bias, uint32_t tmem_base,
                                               uint32_t bar0, int item0, int item1, int q, int lane, int ewarp, int grp) {
     const int sub_r = lane >> 3;
@@ -156,7 +157,21 @@ __device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, const
                             x.z = apply_act<ACT>(x.z + bv.z);
                             x.w = apply_act<ACT>(x.w + bv.w);
                             if (HAS_RES) { x.x += rv[i].x; x.y += rv[i].y; x.z += rv[i].z; x.w += rv[i].w; }
-                            st4(op + (size_t)i * ostep, x);
+                            if (!UP2) {
+                                st4(op + (size_t)i * ostep, x);
+                            } else {
+                                // fused UpSampling2D (nearest x2, reference code/yolo3/model.py:254,274): input pixel
+                                // (b, h, w) -> output pixels (2h..2h+1, 2w..2w+1) of the [B, 2H, 2W, ld_out] tensor
+                                const int m = row0 + sub_r + 4 * i;
+                                const int bi = m / p.rows_per_img, rem = m - bi * p.rows_per_img;
+                                const int h = rem / p.img_w, w = rem - h * p.img_w;
+                                const size_t wo2 = (size_t)2 * p.img_w;
+                                float* d = p.out + (((size_t)bi * 2 * (p.rows_per_img / p.img_w) + 2 * h) * wo2 + 2 * w) * p.ld_out + n;
+                                st4(d, x);
+                                st4(d + p.ld_out, x);
+                                st4(d + wo2 * p.ld_out, x);
+                                st4(d + (wo2 + 1) * p.ld_out, x);
+                            }
                         }
                     }
                 }
@@ -296,6 +311,12 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
     const int item0 = blockIdx.x * p.items_per_cta;
     const int item1 = min(item0 + p.items_per_cta, p.total_items);
 
+    // Everything above touched only this CTA's shared/tensor memory.  The weight producer may start right away (the
+    // weight image is constant); every other role waits for the previous kernel of the stream (programmatic dependent
+    // launch) before it reads activations / gates / residuals or writes the output.
+    if (warp != NUM_THREADS / 32 - 1) pdl_wait();
+    pdl_launch_dependents();
+
     if (warp == 0) {
         // ===== A producer (the weight slots have their own warp, the last one: a full weight ring never holds
         // back the activation prefetch and vice versa) =====
@@ -407,16 +428,19 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
         const bool has_res = p.res != nullptr;
         switch (p.act) {
             case YR_ACT_RELU6:
-                if (has_res) epilogue_loop<YR_ACT_RELU6, true>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                else epilogue_loop<YR_ACT_RELU6, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                if (has_res) epilogue_loop<YR_ACT_RELU6, true, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else if (p.up2) epilogue_loop<YR_ACT_RELU6, false, true>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else epilogue_loop<YR_ACT_RELU6, false, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
                 break;
             case YR_ACT_SWISH:
-                if (has_res) epilogue_loop<YR_ACT_SWISH, true>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                else epilogue_loop<YR_ACT_SWISH, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                if (has_res) epilogue_loop<YR_ACT_SWISH, true, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else if (p.up2) epilogue_loop<YR_ACT_SWISH, false, true>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else epilogue_loop<YR_ACT_SWISH, false, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
                 break;
             default:
-                if (has_res) epilogue_loop<YR_ACT_NONE, true>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                else epilogue_loop<YR_ACT_NONE, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                if (has_res) epilogue_loop<YR_ACT_NONE, true, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else if (p.up2) epilogue_loop<YR_ACT_NONE, false, true>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else epilogue_loop<YR_ACT_NONE, false, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
         }
     }
 
@@ -478,7 +502,8 @@ static bool make_tiling(int K, int N, Tiling& t) {
         // streamed: the MMA issuer waits on weights (L2 latency ~2k cycles against ~800 cycles of MMA per slot), so the
         // weight ring gets the depth (up to 5 slots) and the raw A ring keeps 4 tiles
         t.resident = 0;
-        long long nb = (avail - 4 * tile) / slot;
+        static const int a_keep = getenv("YR_PW_TS_AKEEP") ? atoi(getenv("YR_PW_TS_AKEEP")) : 4;  // tuning knob
+        long long nb = (avail - a_keep * tile) / slot;
         if (nb > 5) nb = 5;
         if (nb > (long long)t.n_tiles * t.KB) nb = (long long)t.n_tiles * t.KB;
         if (nb < 2) nb = 2;
@@ -510,6 +535,9 @@ int launch_pw_ts(const yr_op& op, cudaStream_t s) {
                   (uintptr_t)op.scale) % 16 == 0, "pw_ts: pointers must be 16-byte aligned");
     const long long M = (long long)op.B * op.H * op.W;
     YR_CHECK_ARG(M > 0 && M < (1ll << 31) - 256, "pw_ts: bad row count");
+    YR_CHECK_ARG((op.Ho == op.H && op.Wo == op.W) || (op.Ho == 2 * op.H && op.Wo == 2 * op.W && !op.res),
+                 "pw_ts: output must be HxW, or 2Hx2W (fused nearest upsampling, no residual): got %dx%d for %dx%d", op.Ho, op.Wo,
+                 op.H, op.W);
     ts::Tiling t;
     if (!ts::make_tiling(op.C, op.N, t)) {
         set_error("pw_ts: no tiling for K=%d N=%d", op.C, op.N);
@@ -548,6 +576,8 @@ int launch_pw_ts(const yr_op& op, cudaStream_t s) {
     p.ld_out = op.ld_out;
     p.ld_res = op.ld_res;
     p.rows_per_img = op.H * op.W;
+    p.img_w = op.W;
+    p.up2 = (op.Ho == 2 * op.H && op.Wo == 2 * op.W) ? 1 : 0;
     p.act = op.act;
     p.nA = t.nA;
     p.nT = t.nT;
@@ -581,8 +611,10 @@ int launch_pw_ts(const yr_op& op, cudaStream_t s) {
         cudaMemsetAsync(dbuf, 0, 8 * ts::DBG_EV * sizeof(long long), s);
         p.dbg = dbuf;
     }
-    ts::pw_ts_kernel<<<grid, ts::NUM_THREADS, t.smem, s>>>(tm, p);
-    YR_CHECK_LAUNCH("pw_ts");
+    if (launch_pdl(ts::pw_ts_kernel, dim3(grid), dim3(ts::NUM_THREADS), t.smem, s, tm, p) != cudaSuccess) {
+        set_error("pw_ts: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return YR_ERR_CUDA;
+    }
     if (debug) {
         static long long h[8 * ts::DBG_EV];
         cudaStreamSynchronize(s);

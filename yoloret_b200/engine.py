@@ -61,7 +61,7 @@ class Engine:
                  weights: Dict[str, np.ndarray], anchors: np.ndarray, micro_batch: Optional[int] = None,
                  num_scales: int = 3, max_boxes: int = 20, cand_cap: Optional[int] = None,
                  device: Optional[torch.device] = None, pw_variant: int = _lib.PW_AUTO, input_u8: bool = False,
-                 fuse_se: bool = True, fuse_mbconv: bool = False, lanes: int = 1, autotune: bool = True):
+                 fuse_se: bool = True, fuse_mbconv: bool = False, lanes: int = 1, autotune: bool = True, fuse_up2: bool = True):
         if not torch.cuda.is_available():
             raise _lib.YrError("yoloret_b200.Engine needs a CUDA device (no CPU fallback exists)")
         self.lib = _lib.lib()
@@ -85,6 +85,7 @@ class Engine:
         self.fuse_se = fuse_se
         self.fuse_mbconv = fuse_mbconv
         self.autotune = bool(autotune)
+        self.fuse_up2 = bool(fuse_up2)
         self.cand_cap_arg = cand_cap
         self._check_weights(weights)
         self._alloc()
@@ -242,6 +243,27 @@ class Engine:
         _lib.check(packer(w_kn.data_ptr(), K, N, packed.data_ptr(), self._stream()), "yr_pw_pack")
         return packed
 
+    def _up2_fused_into(self, i: int) -> bool:
+        """True when pointwise layer ``i`` feeds only the nearest-x2 UpSampling2D that follows it (reference
+        code/yolo3/model.py:254,274): the tensor-core kernels then store every output row straight to its four
+        upsampled pixels in the concat slice and the resample op (one launch, one read and one write of the tensor) goes away."""
+        Ls = self.net.layers
+        if not self.fuse_up2 or i + 1 >= len(Ls):
+            return False
+        a, r = Ls[i], Ls[i + 1]
+        if not (a.kind == "pw" and r.kind == "resample" and r.mode == "up2" and a.res is None):
+            return False
+        if not (r.inp[0].buf is a.out.buf and r.inp[0].off == a.out.off and r.inp[0].C == a.out.C):
+            return False
+        if getattr(self, "_consumers", None) is None:
+            self._consumers = {}
+            for L in Ls:
+                for v in L.inp + ([L.res] if L.res is not None else []):
+                    self._consumers[v.buf.name] = self._consumers.get(v.buf.name, 0) + 1
+        if self._consumers.get(a.out.buf.name, 0) != 1 or a.out.buf.full_batch:
+            return False
+        return self._pw_variant_of(i) in (_lib.PW_TC, _lib.PW_TS) and i not in self.mb_blob and (i - 2) not in self.mb_blob
+
     def _pw_variant_of(self, i: int) -> int:
         """Kernel variant layer ``i`` runs with (explicit engine setting, else the autotuner's pick, else the
         first tensor-core kernel that has a tiling, else SIMT)."""
@@ -274,7 +296,7 @@ class Engine:
                 continue
             L = self.net.layers[i]
             key = (L.inp[0].H, L.inp[0].W, L.inp[0].C, L.out.C, L.inp[0].buf.ld, L.out.buf.ld, L.res is not None,
-                   L.gate is not None, L.act)
+                   L.gate is not None, L.act, self._up2_fused_into(i))
             if key not in cache:
                 o = ops[op_of[i]]
                 t = {}
@@ -372,6 +394,14 @@ class Engine:
                     o.res, o.ld_res = _ptr(L.res, chunk0), L.res.buf.ld
                 if L.gate is not None:
                     o.scale = gate_ptr[id(L.gate)]
+                if self._up2_fused_into(i):
+                    up = self.net.layers[i + 1]
+                    o.Ho, o.Wo = up.out.H, up.out.W
+                    o.out, o.ld_out = _ptr(up.out, chunk0), up.out.buf.ld
+                    kind, name, byts, flops, li = meta[-1]
+                    meta[-1] = (kind, name + "+up2", L.bytes_alg + up.out.H * up.out.W * up.out.Clog * 4 - L.out.H * L.out.W * L.out.Clog * 4,
+                                flops, li)
+                    skip = 1
             elif L.kind == "dw":
                 o.kind = _lib.OP_DW
                 if self.se_fused.get(i + 1):
