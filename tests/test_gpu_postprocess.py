@@ -55,7 +55,10 @@ def _run_nms(boxes, scores_per_class, max_boxes, iou_thr, score_thr):
     return [det[0, c, :dc[0, c], 5].view(np.int32).copy() for c in range(Cn)], det, dc
 
 
-@pytest.mark.parametrize("seed,T,quant", [(0, 300, 0), (1, 2000, 64), (2, 5000, 8), (3, 37, 4)])
+@pytest.mark.parametrize("seed,T,quant", [(0, 300, 0), (1, 2000, 64), (2, 5000, 8), (3, 37, 4),
+                                          (4, 10647, 0),      # MAP-mode sized list: shared-memory subset path
+                                          (5, 12000, 4096),   # ... with score ties inside the subset threshold bin
+                                          (6, 6000, 16)])     # ... ties too wide for the subset: plain loop
 def test_nms_bit_exact(built_lib, seed, T, quant):
     """Selected indices identical to the oracle, including score ties (quantised scores),
     degenerate/zero-area boxes and swapped corners."""

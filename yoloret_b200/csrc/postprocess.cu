@@ -227,11 +227,49 @@ __device__ __forceinline__ unsigned long long nms_key(float score, int idx) {
 }
 
 constexpr int NMS_THREADS = 128;
+constexpr int NMS_FAST_MIN = 1024;   // lists longer than this try the shared-memory subset first
+constexpr int NMS_CAP = 1024;        // subset capacity: 8 KB of keys + 16 KB of boxes
+constexpr int NMS_TARGET = 256;      // the subset holds at least this many of the best candidates
+
+__device__ __forceinline__ unsigned nms_u32(float score) {
+    const unsigned u = __float_as_uint(score);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // order-preserving map of fp32 -> u32
+}
+
+// block-wide maximum of a 64-bit key (all threads get it)
+__device__ __forceinline__ unsigned long long nms_block_max(unsigned long long best, unsigned long long* s_key,
+                                                            unsigned long long* s_best) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+    }
+    if (lane == 0) s_key[warp] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long m = s_key[0];
+#pragma unroll
+        for (int w = 1; w < NMS_THREADS / 32; ++w) m = s_key[w] > m ? s_key[w] : m;
+        *s_best = m;
+    }
+    __syncthreads();
+    const unsigned long long r = *s_best;
+    __syncthreads();  // s_key / s_best are rewritten by the next call
+    return r;
+}
 
 // Greedy NMS as 'repeat: pick the best alive candidate (score desc, index asc), kill
 // everything with IoU > thr against it'.  This selects exactly the boxes, in exactly the
 // order, of the sequential priority-queue algorithm: a candidate is selected iff no
 // earlier-selected box suppresses it, and candidates are visited by (score, index).
+//
+// Long lists (MAP mode runs with score_threshold = 0: every one of the 10 647 boxes is a candidate of every class,
+// reference code/main.py:175) first run the same loop on a SUBSET held in shared memory: all candidates whose score
+// is >= a threshold found with a two-level 8-bit histogram so that the subset holds the >= 256 best.  Greedy NMS
+// visits candidates in key order, so as long as it stops (max_boxes selected) before the subset is exhausted, the
+// rest of the list can never be looked at and the result is exactly that of the full list.  If the subset runs out
+// first, the remaining candidates are filtered against everything selected so far and the plain loop continues.
 __global__ void __launch_bounds__(NMS_THREADS)
 nms_kernel(const float* __restrict__ boxes, int total_boxes, float* __restrict__ cand_score,
            const int32_t* __restrict__ cand_index, const int32_t* __restrict__ cand_count, int C, int cand_cap,
@@ -239,6 +277,10 @@ nms_kernel(const float* __restrict__ boxes, int total_boxes, float* __restrict__
            int32_t* __restrict__ status) {
     __shared__ unsigned long long s_key[NMS_THREADS / 32];
     __shared__ unsigned long long s_best;
+    __shared__ unsigned s_hist[256];
+    __shared__ unsigned s_sel[4];  // bin, count above the bin, count including the bin, subset size
+    __shared__ unsigned long long sub_key[NMS_CAP];
+    __shared__ float4 sub_box[NMS_CAP];
     const int c = blockIdx.x, b = blockIdx.y;
     const size_t list = (size_t)b * C + c;
     int n = cand_count[list];
@@ -250,15 +292,125 @@ nms_kernel(const float* __restrict__ boxes, int total_boxes, float* __restrict__
     const int32_t* ix = cand_index + list * cand_cap;
     const float4* bx = reinterpret_cast<const float4*>(boxes) + (size_t)b * total_boxes;
     float* out = det + list * max_boxes * 6;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = threadIdx.x;
+
+    auto emit = [&](int k, unsigned long long best, float4 sel, int sel_idx) {  // thread 0 only
+        unsigned u = (unsigned)(best >> 32);
+        u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+        out[k * 6 + 0] = sel.x;
+        out[k * 6 + 1] = sel.y;
+        out[k * 6 + 2] = sel.z;
+        out[k * 6 + 3] = sel.w;
+        out[k * 6 + 4] = __uint_as_float(u);
+        out[k * 6 + 5] = __int_as_float(sel_idx);
+    };
 
     int k = 0;
+    if (n > NMS_FAST_MIN) {
+        // ---- threshold: largest 16-bit score prefix P with count(prefix >= P) >= NMS_TARGET, if that count fits
+        unsigned prefix = 0;
+        bool have = false;
+        for (int level = 0; level < 2; ++level) {
+            for (int i = tid; i < 256; i += NMS_THREADS) s_hist[i] = 0;
+            __syncthreads();
+            const unsigned hi = s_sel[0];  // bin of level 0 (valid at level 1)
+            for (int i = tid; i < n; i += NMS_THREADS) {
+                const unsigned u = nms_u32(sc[i]);
+                if (level == 0) atomicAdd(&s_hist[u >> 24], 1u);
+                else if ((u >> 24) == hi) atomicAdd(&s_hist[(u >> 16) & 0xffu], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned above = level == 0 ? 0u : s_sel[1], cum = above;
+                int bin = 255;
+                for (; bin > 0; --bin) {
+                    if (cum + s_hist[bin] >= (unsigned)NMS_TARGET) break;
+                    cum += s_hist[bin];
+                }
+                s_sel[0] = (unsigned)bin;
+                s_sel[1] = cum;                 // strictly above this bin
+                s_sel[2] = cum + s_hist[bin];   // including it
+            }
+            __syncthreads();
+            const unsigned bin = s_sel[0], incl = s_sel[2];
+            if (level == 0) {
+                prefix = bin << 24;
+                if (incl <= (unsigned)NMS_CAP) { have = true; break; }
+            } else {
+                prefix |= bin << 16;
+                have = incl <= (unsigned)NMS_CAP;
+            }
+            __syncthreads();
+        }
+        if (have) {
+            // ---- subset -> shared memory (any order: the arg-max below is order independent)
+            if (tid == 0) s_sel[3] = 0;
+            __syncthreads();
+            for (int i = tid; i < n; i += NMS_THREADS) {
+                const float sv = sc[i];
+                if (nms_u32(sv) >= prefix) {
+                    const int id = ix[i];
+                    const unsigned pos = atomicAdd(&s_sel[3], 1u);
+                    sub_key[pos] = nms_key(sv, id);
+                    sub_box[pos] = __ldg(bx + id);
+                }
+            }
+            __syncthreads();
+            const int m = (int)s_sel[3];
+            float4 sel = make_float4(0.f, 0.f, 0.f, 0.f);
+            bool have_sel = false;
+            bool exhausted = false;
+            while (true) {
+                unsigned long long best = 0ull;
+                for (int i = tid; i < m; i += NMS_THREADS) {
+                    const unsigned long long key = sub_key[i];
+                    if (key == 0ull) continue;
+                    if (have_sel && iou_tf(sub_box[i], sel) > iou_thr) {
+                        sub_key[i] = 0ull;
+                        continue;
+                    }
+                    best = key > best ? key : best;
+                }
+                best = nms_block_max(best, s_key, &s_best);
+                if (best == 0ull) { exhausted = true; break; }
+                const int sel_idx = (int)(0xffffffffu - (unsigned)(best & 0xffffffffull));
+                sel = __ldg(bx + sel_idx);
+                have_sel = true;
+                for (int i = tid; i < m; i += NMS_THREADS)
+                    if (sub_key[i] == best) sub_key[i] = 0ull;  // the selected one leaves the list
+                if (tid == 0) emit(k, best, sel, sel_idx);
+                ++k;
+                if (k >= max_boxes) break;
+                __syncthreads();
+            }
+            if (!exhausted) {
+                if (tid == 0) det_count[list] = k;
+                return;
+            }
+            // ---- subset exhausted before max_boxes: drop it from the list, filter the rest against the selections
+            __syncthreads();  // the selections written by thread 0 are visible to the block
+            for (int i = tid; i < n; i += NMS_THREADS) {
+                const float sv = sc[i];
+                bool dead = nms_u32(sv) >= prefix;
+                if (!dead) {
+                    const float4 bb = __ldg(bx + ix[i]);
+                    for (int j = 0; j < k && !dead; ++j) {
+                        const float4 sj = make_float4(out[j * 6 + 0], out[j * 6 + 1], out[j * 6 + 2], out[j * 6 + 3]);
+                        dead = iou_tf(bb, sj) > iou_thr;
+                    }
+                }
+                if (dead) sc[i] = -INFINITY;
+            }
+            __syncthreads();
+        }
+    }
+
     float4 sel = make_float4(0.f, 0.f, 0.f, 0.f);
     int sel_idx = -1;
-    while (n > 0) {
+    while (n > 0 && k < max_boxes) {
         // pass: apply the previous selection's suppression, find the best survivor
         unsigned long long best = 0ull;
-        for (int i = threadIdx.x; i < n; i += NMS_THREADS) {
+        for (int i = tid; i < n; i += NMS_THREADS) {
             float s = sc[i];
             if (s == -INFINITY) continue;
             const int id = ix[i];
@@ -271,39 +423,14 @@ nms_kernel(const float* __restrict__ boxes, int total_boxes, float* __restrict__
             const unsigned long long key = nms_key(s, id);
             best = key > best ? key : best;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-            best = other > best ? other : best;
-        }
-        if (lane == 0) s_key[warp] = best;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned long long m = s_key[0];
-#pragma unroll
-            for (int w = 1; w < NMS_THREADS / 32; ++w) m = s_key[w] > m ? s_key[w] : m;
-            s_best = m;
-        }
-        __syncthreads();
-        best = s_best;
+        best = nms_block_max(best, s_key, &s_best);
         if (best == 0ull) break;
         sel_idx = (int)(0xffffffffu - (unsigned)(best & 0xffffffffull));
         sel = __ldg(bx + sel_idx);
-        if (threadIdx.x == 0) {
-            unsigned u = (unsigned)(best >> 32);
-            u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
-            out[k * 6 + 0] = sel.x;
-            out[k * 6 + 1] = sel.y;
-            out[k * 6 + 2] = sel.z;
-            out[k * 6 + 3] = sel.w;
-            out[k * 6 + 4] = __uint_as_float(u);
-            out[k * 6 + 5] = __int_as_float(sel_idx);
-        }
+        if (tid == 0) emit(k, best, sel, sel_idx);
         ++k;
-        if (k >= max_boxes) break;
-        __syncthreads();  // s_best is rewritten next round
     }
-    if (threadIdx.x == 0) det_count[list] = k;
+    if (tid == 0) det_count[list] = k;
 }
 
 __global__ void pack_kernel(const float* __restrict__ det, const int32_t* __restrict__ det_count, int C, int max_boxes,

@@ -502,8 +502,7 @@ static bool make_tiling(int K, int N, Tiling& t) {
         // streamed: the MMA issuer waits on weights (L2 latency ~2k cycles against ~800 cycles of MMA per slot), so the
         // weight ring gets the depth (up to 5 slots) and the raw A ring keeps 4 tiles
         t.resident = 0;
-        static const int a_keep = getenv("YR_PW_TS_AKEEP") ? atoi(getenv("YR_PW_TS_AKEEP")) : 4;  // tuning knob
-        long long nb = (avail - a_keep * tile) / slot;
+        long long nb = (avail - 4 * tile) / slot;  // measured: a 2-tile A ring with one more weight slot is slower
         if (nb > 5) nb = 5;
         if (nb > (long long)t.n_tiles * t.KB) nb = (long long)t.n_tiles * t.KB;
         if (nb < 2) nb = 2;
