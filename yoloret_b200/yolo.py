@@ -46,6 +46,7 @@ class YoloModel:
         else:
             self.model.load_weights(self.model_path, anchors=anchors)
         self.engine = self.model.engine
+        self._graph = None
         if not quiet:
             print(self.model_path)
 
@@ -66,7 +67,9 @@ class YoloModel:
             raise ValueError("engine built for uint8 batches; detect_image needs a float32 engine")
         e.input[0].copy_(lb)
         e.pp.set_image_shapes(shape)
-        e.step(self.score, self.nms)
+        if self._graph is None:  # the ~90 launches of a step replay as one CUDA graph from the second image on
+            self._graph = e.capture(self.score, self.nms)
+        self._graph.replay()
         boxes, scores, classes = e.results()[0]
         if self.with_classes:
             classes = np.asarray([self.classes[c].encode() for c in classes])
