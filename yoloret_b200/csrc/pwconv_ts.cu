@@ -118,6 +118,7 @@ __device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, const
             const int rows = min(32, p.M - row0);
             const uint32_t tsrc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.acc_stride;
             bool waited = false;
+            float v[32];
             for (int c0 = 0; c0 < ncols; c0 += 32) {
                 const int c = c0 + sub_c;
                 const int n = nt * p.BN + c;
@@ -135,13 +136,16 @@ __device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, const
                     tc_fence_after();
                     waited = true;
                     if (ewarp == 0 && lane == 0) dbg_mark(p, 6, it);
+                    if (!HAS_RES) tmem_ld32_issue(tsrc + c0, v);
                 }
-                float v[32];
-                tmem_ld32(tsrc + c0, v);
+                if (HAS_RES) tmem_ld32_issue(tsrc + c0, v);  // residual variant: no prefetch (register budget)
+                tmem_ld_wait();  // this chunk's accumulator columns are in v
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<float4*>(stg + lane * EPI_LD + 4 * j) =
                         make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                // v now lives in shared memory: fetch the next chunk into the same registers while this one is stored
+                if (!HAS_RES && c0 + 32 < ncols) tmem_ld32_issue(tsrc + c0 + 32, v);
                 __syncwarp();
                 if (col_ok) {
                     const float4 bv = *reinterpret_cast<const float4*>(s_bias + n);

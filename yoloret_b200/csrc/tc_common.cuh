@@ -77,7 +77,10 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+// 32 consecutive TMEM columns of this thread's lane -> registers.  The load is asynchronous: the registers are valid
+// only after tmem_ld_wait(), so an epilogue can issue the load of its next chunk and hide the TMEM latency behind the
+// stores of the current one.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -89,7 +92,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    tmem_ld32_issue(taddr, v);
+    tmem_ld_wait();
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row groups 1024 B apart).
