@@ -601,10 +601,11 @@ int launch_pw_ts(const yr_op& op, cudaStream_t s) {
         attr_set = true;
     }
     const int max_ctas = tc::num_sms();
-    // whole 128-row blocks per CTA (all n tiles of a block stay on one SM so the A re-read hits L2)
-    const int blocks_per_cta = (p.m_tiles + max_ctas - 1) / max_ctas;
-    p.items_per_cta = blocks_per_cta * p.n_tiles;
-    const int grid = (p.m_tiles + blocks_per_cta - 1) / blocks_per_cta;
+    // contiguous runs of m-major items per CTA: the n tiles of a 128-row block are mostly on one SM (the A re-read hits
+    // L2 either way), and the split is item- not block-granular, which fills more SMs when there are few row blocks
+    // (26x26 x 64 images = 338 blocks x 2 n tiles: 136 CTAs x 5 items instead of 113 x 6)
+    p.items_per_cta = (p.total_items + max_ctas - 1) / max_ctas;
+    const int grid = (p.total_items + p.items_per_cta - 1) / p.items_per_cta;
     p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(t.BN >> 3) << 17) | ((uint32_t)(ts::BM >> 4) << 24);
     p.dbg = nullptr;
     static const bool debug = getenv("YR_PW_TC_DEBUG") != nullptr;  // developer aid only: timeline of CTA 0
