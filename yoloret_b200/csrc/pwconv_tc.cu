@@ -340,7 +340,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
         // ===== MMA issuer: the whole warp runs the loop converged (addresses stay in uniform registers);
         // one elected lane issues the tcgen05 instructions =====
         Ring ra, rl, rb, racc;
-        uint32_t dq = 0;
+        uint32_t dq = 0, b_seen = 0;
         // descriptors differ only in the 14-bit start-address field: build one, then add (bytes >> 4)
         const uint64_t desc0 = make_desc_sw128(base);
         const int k_tail = (p.K - (p.KB - 1) * BK + 7) / 8;  // 8-wide K steps of the last k-block
@@ -354,7 +354,10 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
                 uint32_t slot;
                 if (p.resident) {
                     slot = kb;
-                    mbar_wait(bar0 + 8u * (BAR_B_FULL + slot), 0, 3);
+                    if (!((b_seen >> slot) & 1u)) {  // a resident slot lands once: no barrier round trip after that
+                        mbar_wait(bar0 + 8u * (BAR_B_FULL + slot), 0, 3);
+                        b_seen |= 1u << slot;
+                    }
                 } else {
                     slot = rb.slot;
                     mbar_wait(bar0 + 8u * (BAR_B_FULL + slot), rb.phase, 3);

@@ -372,7 +372,7 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
     } else if (warp == 1) {
         // ===== MMA issuer (whole warp converged, one elected lane issues) =====
         Ring rt, rb, racc;
-        uint32_t dq = 0;
+        uint32_t dq = 0, b_seen = 0;
         const uint64_t desc0 = make_desc_sw128(base);
         const int k_tail = (p.K - (p.KB - 1) * BK + 7) / 8;
         int nt = item0 % p.n_tiles;
@@ -383,7 +383,10 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
                 uint32_t slot;
                 if (p.resident) {
                     slot = (uint32_t)(nt * p.KB + kb);
-                    mbar_wait(bar0 + 8u * (BAR_B_FULL + slot), 0, 3);
+                    if (!((b_seen >> slot) & 1u)) {  // a resident slot lands once: no barrier round trip after that
+                        mbar_wait(bar0 + 8u * (BAR_B_FULL + slot), 0, 3);
+                        b_seen |= 1u << slot;
+                    }
                 } else {
                     slot = rb.slot;
                     mbar_wait(bar0 + 8u * (BAR_B_FULL + slot), rb.phase, 3);
