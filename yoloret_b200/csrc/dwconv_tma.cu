@@ -321,7 +321,7 @@ int launch_dw_tma(const yr_op& op, cudaStream_t s) {
     const cuuint32_t box[4] = {(cuuint32_t)pl.cb, (cuuint32_t)pl.IW, (cuuint32_t)pl.IH, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(op.in), gdim, gstr, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, tc::l2_promotion(),
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) {
         set_error("dw_tma: cuTensorMapEncodeTiled failed (%d) for C=%d H=%d W=%d ld=%d box %dx%dx%d", (int)cr, op.C, op.H,

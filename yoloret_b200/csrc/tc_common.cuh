@@ -149,6 +149,15 @@ inline EncodeTiledFn encode_tiled() {
     return fn;
 }
 
+// L2 promotion of the activation tensor maps (experiment knob YR_TMA_L2PROMO = 0 none / 1 128 B / 2 256 B).
+inline CUtensorMapL2promotion l2_promotion() {
+    static const int v = [] {
+        const char* e = getenv("YR_TMA_L2PROMO");
+        return e ? atoi(e) : 1;
+    }();
+    return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : (v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+}
+
 inline int num_sms() {
     static int n = 0;
     if (n == 0) {
