@@ -228,7 +228,7 @@ __device__ __forceinline__ unsigned long long nms_key(float score, int idx) {
 
 constexpr int NMS_THREADS = 128;
 constexpr int NMS_FAST_MIN = 1024;   // lists longer than this try the shared-memory subset first
-constexpr int NMS_CAP = 1024;        // subset capacity: 8 KB of keys + 16 KB of boxes
+constexpr int NMS_CAP = 512;         // subset capacity: 4 KB of keys + 8 KB of boxes (static smem: keeps 16 CTAs per SM)
 constexpr int NMS_TARGET = 256;      // the subset holds at least this many of the best candidates
 
 __device__ __forceinline__ unsigned nms_u32(float score) {
