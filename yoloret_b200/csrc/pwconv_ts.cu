@@ -75,9 +75,15 @@ constexpr int BAR_COUNT = BAR_ACC_EMPTY + MAX_ACC;
 static_assert(BAR_COUNT * 8 + 8 <= BAR_BYTES, "barrier table overflows its reservation");
 
 constexpr int DBG_EV = 256;
-__device__ __forceinline__ void dbg_mark(const Params& p, int role, uint32_t idx) {
-    if (p.dbg != nullptr && blockIdx.x == 0 && idx < DBG_EV) p.dbg[role * DBG_EV + idx] = clock64();
+// The timeline marks are compiled in only for the debug instantiation of the kernel (YR_PW_TC_DEBUG=1): in the MMA
+// issuer's serial loop even a predicated-off clock read and store are instructions on the critical path.
+template <bool DBG>
+__device__ __forceinline__ void dbg_mark_t(const Params& p, int role, uint32_t idx) {
+    if (DBG) {
+        if (p.dbg != nullptr && blockIdx.x == 0 && idx < DBG_EV) p.dbg[role * DBG_EV + idx] = clock64();
+    }
 }
+#define dbg_mark(p, role, idx) dbg_mark_t<DBG>(p, role, idx)
 
 // tcgen05.mma with the A operand in tensor memory (lane = tile row, one TF32 element per column)
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc,
@@ -102,7 +108,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- epilogue (see pwconv_tc.cu for the access pattern; items here are m-major) ---------------
-template <int ACT, bool HAS_RES, bool UP2>
+template <int ACT, bool HAS_RES, bool UP2, bool DBG>
 __device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, const float* s_bias, uint32_t tmem_base,
                                               uint32_t bar0, int item0, int item1, int q, int lane, int ewarp, int grp) {
     const int sub_r = lane >> 3;
@@ -197,7 +203,7 @@ __device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, const
 // ---- converters: raw fp32 A tile (smem) -> (hi, lo) TF32 columns of a TMEM stage ----------------
 // Thread = tile row r = its TMEM lane.  The 128-byte row is read as 8 LDS.128 whose chunk index is
 // XORed with (r & 7) (the TMA swizzle): the 8 lanes of a quarter-warp hit 8 different bank groups.
-template <bool HAS_SCALE>
+template <bool HAS_SCALE, bool DBG>
 __device__ __forceinline__ void converter_loop(const Params& p, const uint8_t* a_ring, uint32_t tmem_base, uint32_t bar0,
                                                int item0, int item1, int q, int lane, int grp) {
     Ring ra, rt;
@@ -266,6 +272,7 @@ __device__ __forceinline__ void converter_loop(const Params& p, const uint8_t* a
     }
 }
 
+template <bool DBG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -421,8 +428,8 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
         }
     } else if (warp < 2 + NUM_CONVERTERS / 32) {
         const int cw = warp - 2;
-        if (p.scale != nullptr) converter_loop<true>(p, gbase + a_off, tmem_base, bar0, item0, item1, warp & 3, lane, cw >> 2);
-        else converter_loop<false>(p, gbase + a_off, tmem_base, bar0, item0, item1, warp & 3, lane, cw >> 2);
+        if (p.scale != nullptr) converter_loop<true, DBG>(p, gbase + a_off, tmem_base, bar0, item0, item1, warp & 3, lane, cw >> 2);
+        else converter_loop<false, DBG>(p, gbase + a_off, tmem_base, bar0, item0, item1, warp & 3, lane, cw >> 2);
     } else if (warp < 2 + (NUM_CONVERTERS + NUM_EPILOGUE) / 32) {
         // ===== epilogue =====
         const int ew8 = warp - (2 + NUM_CONVERTERS / 32);
@@ -435,19 +442,19 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
         const bool has_res = p.res != nullptr;
         switch (p.act) {
             case YR_ACT_RELU6:
-                if (has_res) epilogue_loop<YR_ACT_RELU6, true, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                else if (p.up2) epilogue_loop<YR_ACT_RELU6, false, true>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                else epilogue_loop<YR_ACT_RELU6, false, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                if (has_res) epilogue_loop<YR_ACT_RELU6, true, false, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else if (p.up2) epilogue_loop<YR_ACT_RELU6, false, true, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else epilogue_loop<YR_ACT_RELU6, false, false, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
                 break;
             case YR_ACT_SWISH:
-                if (has_res) epilogue_loop<YR_ACT_SWISH, true, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                else if (p.up2) epilogue_loop<YR_ACT_SWISH, false, true>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                else epilogue_loop<YR_ACT_SWISH, false, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                if (has_res) epilogue_loop<YR_ACT_SWISH, true, false, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else if (p.up2) epilogue_loop<YR_ACT_SWISH, false, true, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else epilogue_loop<YR_ACT_SWISH, false, false, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
                 break;
             default:
-                if (has_res) epilogue_loop<YR_ACT_NONE, true, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                else if (p.up2) epilogue_loop<YR_ACT_NONE, false, true>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                else epilogue_loop<YR_ACT_NONE, false, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                if (has_res) epilogue_loop<YR_ACT_NONE, true, false, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else if (p.up2) epilogue_loop<YR_ACT_NONE, false, true, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else epilogue_loop<YR_ACT_NONE, false, false, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
         }
     }
 
@@ -596,8 +603,10 @@ int launch_pw_ts(const yr_op& op, cudaStream_t s) {
     p.total_items = p.n_tiles * p.m_tiles;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(ts::pw_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM_LIMIT) !=
-            cudaSuccess) {
+        if (cudaFuncSetAttribute(ts::pw_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM_LIMIT) !=
+                cudaSuccess ||
+            cudaFuncSetAttribute(ts::pw_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM_LIMIT) !=
+                cudaSuccess) {
             set_error("pw_ts: cannot raise the dynamic shared memory limit: %s", cudaGetErrorString(cudaGetLastError()));
             return YR_ERR_CUDA;
         }
@@ -618,7 +627,8 @@ int launch_pw_ts(const yr_op& op, cudaStream_t s) {
         cudaMemsetAsync(dbuf, 0, 8 * ts::DBG_EV * sizeof(long long), s);
         p.dbg = dbuf;
     }
-    if (launch_pdl(ts::pw_ts_kernel, dim3(grid), dim3(ts::NUM_THREADS), t.smem, s, tm, p) != cudaSuccess) {
+    if (launch_pdl(debug ? ts::pw_ts_kernel<true> : ts::pw_ts_kernel<false>, dim3(grid), dim3(ts::NUM_THREADS), t.smem, s, tm,
+                   p) != cudaSuccess) {
         set_error("pw_ts: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         return YR_ERR_CUDA;
     }
