@@ -66,9 +66,14 @@ constexpr int BAR_COUNT = BAR_ACC_EMPTY + MAX_ACC;
 static_assert(BAR_COUNT * 8 + 8 <= BAR_BYTES, "barrier table overflows its reservation");
 
 constexpr int DBG_EV = 256;  // events per role in the debug timeline
-__device__ __forceinline__ void dbg_mark(const Params& p, int role, uint32_t idx) {
-    if (p.dbg != nullptr && blockIdx.x == 0 && idx < DBG_EV) p.dbg[role * DBG_EV + idx] = clock64();
+// compiled in only for the debug instantiation of the kernel (YR_PW_TC_DEBUG=1); see pwconv_ts.cu
+template <bool DBG>
+__device__ __forceinline__ void dbg_mark_t(const Params& p, int role, uint32_t idx) {
+    if (DBG) {
+        if (p.dbg != nullptr && blockIdx.x == 0 && idx < DBG_EV) p.dbg[role * DBG_EV + idx] = clock64();
+    }
 }
+#define dbg_mark(p, role, idx) dbg_mark_t<DBG>(p, role, idx)
 
 // Streamed-weight layers walk their tiles in GROUPS of two consecutive M tiles of one n tile: each weight slot
 // is fetched once per group and feeds the k-block of both tiles, which halves the L2 -> SM weight traffic that
@@ -82,7 +87,7 @@ __device__ __forceinline__ int group_size(const Params& p, int item, int item1, 
 // One warp owns TMEM lane quarter q (32 tile rows).  Per 32-column chunk: the accumulator row a lane
 // holds goes to smem as 8 STS.128 (row stride 36 floats: conflict-free per 8-lane phase), comes back
 // as LDS.128 with 8 lanes covering one row, and leaves as STG.128: 4 full 128-byte lines per store.
-template <int ACT, bool HAS_RES, bool UP2>
+template <int ACT, bool HAS_RES, bool UP2, bool DBG>
 __device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, float* s_bias, uint32_t tmem_base,
                                               uint32_t bar0, int item0, int item1, int q, int lane, int ewarp, int grp) {
     const int sub_r = lane >> 3;        // row within a 4-row group
@@ -190,7 +195,7 @@ __device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, float
 // ---- converters: raw fp32 A tile -> (hi, lo) TF32 tiles; the SE gate is folded in here -------------
 // 8 warps; each thread owns 4 of the tile's 1024 16-byte chunks.  hi overwrites the raw tile in place
 // (an elementwise map keeps the TMA swizzle), lo goes to a slot of the short lo ring.
-template <bool HAS_SCALE>
+template <bool HAS_SCALE, bool DBG>
 __device__ __forceinline__ void converter_loop(const Params& p, uint8_t* gbase, uint32_t a_off, uint32_t l_off,
                                                uint32_t bar0, int item0, int item1, int ct, int grp) {
     Ring ra, rl;
@@ -250,6 +255,7 @@ __device__ __forceinline__ void converter_loop(const Params& p, uint8_t* gbase, 
 }
 
 // ---- the GEMM ------------------------------------------------------------------------------
+template <bool DBG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -404,8 +410,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
         }
     } else if (warp < 2 + NUM_CONVERTERS / 32) {
         const int ct = (threadIdx.x - 64) & 127, cg = (threadIdx.x - 64) >> 7;  // thread within group, group
-        if (p.scale != nullptr) converter_loop<true>(p, gbase, a_off, l_off, bar0, item0, item1, ct, cg);
-        else converter_loop<false>(p, gbase, a_off, l_off, bar0, item0, item1, ct, cg);
+        if (p.scale != nullptr) converter_loop<true, DBG>(p, gbase, a_off, l_off, bar0, item0, item1, ct, cg);
+        else converter_loop<false, DBG>(p, gbase, a_off, l_off, bar0, item0, item1, ct, cg);
     } else {
         // ===== epilogue =====
         const int ew8 = warp - (2 + NUM_CONVERTERS / 32);  // 0..7
@@ -416,19 +422,19 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
         const bool has_res = p.res != nullptr;
         switch (p.act) {
             case YR_ACT_RELU6:
-                if (has_res) epilogue_loop<YR_ACT_RELU6, true, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                else if (p.up2) epilogue_loop<YR_ACT_RELU6, false, true>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                else epilogue_loop<YR_ACT_RELU6, false, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                if (has_res) epilogue_loop<YR_ACT_RELU6, true, false, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else if (p.up2) epilogue_loop<YR_ACT_RELU6, false, true, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else epilogue_loop<YR_ACT_RELU6, false, false, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
                 break;
             case YR_ACT_SWISH:
-                if (has_res) epilogue_loop<YR_ACT_SWISH, true, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                else if (p.up2) epilogue_loop<YR_ACT_SWISH, false, true>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                else epilogue_loop<YR_ACT_SWISH, false, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                if (has_res) epilogue_loop<YR_ACT_SWISH, true, false, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else if (p.up2) epilogue_loop<YR_ACT_SWISH, false, true, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else epilogue_loop<YR_ACT_SWISH, false, false, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
                 break;
             default:
-                if (has_res) epilogue_loop<YR_ACT_NONE, true, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                else if (p.up2) epilogue_loop<YR_ACT_NONE, false, true>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                else epilogue_loop<YR_ACT_NONE, false, false>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                if (has_res) epilogue_loop<YR_ACT_NONE, true, false, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else if (p.up2) epilogue_loop<YR_ACT_NONE, false, true, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+                else epilogue_loop<YR_ACT_NONE, false, false, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
         }
         }
     }
@@ -606,8 +612,10 @@ int launch_pw_tc(const yr_op& op, cudaStream_t s) {
     p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(t.BN >> 3) << 17) | ((uint32_t)(tc::BM >> 4) << 24);
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(tc::pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT) !=
-            cudaSuccess) {
+        if (cudaFuncSetAttribute(tc::pw_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT) !=
+                cudaSuccess ||
+            cudaFuncSetAttribute(tc::pw_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT) !=
+                cudaSuccess) {
             set_error("pw_tc: cannot raise the dynamic shared memory limit: %s", cudaGetErrorString(cudaGetLastError()));
             return YR_ERR_CUDA;
         }
@@ -621,7 +629,8 @@ int launch_pw_tc(const yr_op& op, cudaStream_t s) {
         cudaMemsetAsync(dbuf, 0, 8 * tc::DBG_EV * sizeof(long long), s);
         p.dbg = dbuf;
     }
-    if (launch_pdl(tc::pw_tc_kernel, dim3(grid), dim3(tc::NUM_THREADS), t.smem, s, tm, p) != cudaSuccess) {
+    if (launch_pdl(debug ? tc::pw_tc_kernel<true> : tc::pw_tc_kernel<false>, dim3(grid), dim3(tc::NUM_THREADS), t.smem, s, tm,
+                   p) != cudaSuccess) {
         set_error("pw_tc: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         return YR_ERR_CUDA;
     }
