@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--lanes", type=int, default=1, help="concurrent micro-batch lanes (streams) inside a step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the oracle check of the workload's batch")
     ap.add_argument("--ref-images", type=int, default=4, help="images per step of the reference arm")
     ap.add_argument("--ncu-step", action="store_true",
                     help="profiling aid: run ONE eager step between cudaProfilerStart/Stop and exit "
@@ -231,12 +232,41 @@ def run_reference(a):
 
 
 # ---------------------------------------------------------------------------------------------
+def quantise_u8(x):
+    """float32 images in [0,1] -> the uint8 images a decoder would deliver (round to nearest)."""
+    import torch
+    return torch.clamp(torch.round(x * 255.0), 0, 255).to(torch.uint8)
+
+
+ARITH = ("pointwise 1x1: 3xTF32 products (tcgen05 kind::tf32 on a hi/lo split of both operands, ~21 mantissa bits), "
+         "fp32 accumulation in TMEM; everything else fp32 SIMT; fp32 storage")
+
+
+def verify_against_oracle(a, yolo, weights, anchors, x_host, xu_host):
+    """Outside every timed region: the engine's results for THIS workload's batch against the CPU oracle on four
+    images spread over the batch (oracle/verify.py: head logits, post-process on identical inputs, end to end), for
+    the float32 batch and for the uint8 batch the e2e leg uploads."""
+    from oracle import verify as overify
+    B = a.batch
+    sample = sorted({0, B // 3, (2 * B) // 3, B - 1})
+    rep = {}
+    try:
+        for tag, host, ref_x in (("f32", x_host, x_host), ("u8", xu_host, xu_host.float() * (1.0 / 255.0))):
+            dets = yolo.detect_batch(host)
+            logits = [y.cpu().numpy() for y in yolo.engine.raw_outputs()]
+            rep[tag] = overify.verify_batch(weights, ref_x, a.model, a.classes, anchors, logits, dets, sample, SCORE, IOU)
+        return True, rep
+    except AssertionError as e:  # report, do not hide: the line then says "verified": false
+        rep["error"] = str(e)[:400]
+        return False, rep
+
+
 def run_b200(a):
     import numpy as np
     import torch
     import torch.distributed as dist
     from yoloret_b200.yolo import YOLO
-    from yoloret_b200 import parallel
+    from yoloret_b200 import parallel, _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -266,19 +296,22 @@ def run_b200(a):
     eng = yolo.engine
     gather = parallel.DetectionGather(eng.pp, world, rank) if world > 1 else None
 
-    # rank-distinct synthetic images, pinned on the host for the e2e leg
+    # rank-distinct synthetic images, pinned on the host for the e2e legs: float32 in [0,1] (the workload as
+    # SURVEY.md section 8d states it) and the same images as uint8 (what an image decoder hands to the reference,
+    # code/yolo.py:106 - the stem kernel applies the 1/255)
     x_host = make_inputs(a, a.batch, 1234 + rank).pin_memory()
-    eng.input.copy_(x_host, non_blocking=True)
+    xu_host = quantise_u8(x_host).pin_memory()
+    eng.input_slot(0, False).copy_(x_host, non_blocking=True)
     eng.pp.set_image_shapes((a.size, a.size))
     if a.ncu_step:
-        eng.step(SCORE, IOU)
+        eng.step(SCORE, IOU, 0, False)
         torch.cuda.synchronize(dev)
         torch.cuda.profiler.start()
-        eng.step(SCORE, IOU)
+        eng.step(SCORE, IOU, 0, False)
         torch.cuda.synchronize(dev)
         torch.cuda.profiler.stop()
         return
-    graph = eng.capture(SCORE, IOU)
+    graph = eng.capture(SCORE, IOU, 0, False)
     launches_per_step = eng.launches_per_forward
 
     def barrier():
@@ -288,12 +321,14 @@ def run_b200(a):
 
     def device_step():
         graph.replay()
-        if gather is not None:
-            gather.all_gather()
+        if gather is not None:  # side stream: overlaps the next replay; joined before the closing event
+            gather.gather_async(read=False)
 
     # ---- value: inputs resident in HBM -----------------------------------------------------
     for _ in range(max(a.warmup, 3)):
         device_step()
+    if gather is not None:
+        gather.join()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -304,6 +339,8 @@ def run_b200(a):
     e0.record()
     for _ in range(a.steps):
         device_step()
+    if gather is not None:
+        gather.join()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -311,27 +348,29 @@ def run_b200(a):
 
     # ---- e2e: public API, host buffers, H2D + D2H inside -------------------------------------
     # YOLO.detect_stream: every step uploads its batch from pinned host memory, computes, and reads its
-    # detections back; the upload of step i+1 overlaps the compute of step i (double-buffered input).
-    def e2e_run(n):
-        for _res in yolo.detect_stream((x_host for _ in range(n)), unpack=False):
-            if gather is not None:
-                gather.all_gather()
-                if rank == 0:
-                    gather.read()
+    # detections back; the upload of step i+1 overlaps the compute of step i (double-buffered input).  Multi-GPU:
+    # every step also all-gathers the ranks' detections (side stream) and rank 0 reads ALL ranks' detections back.
+    def e2e_run(n, host):
+        for _res in yolo.detect_stream((host for _ in range(n)), unpack=False, gather=gather, gather_read=(rank == 0)):
+            pass
 
     def e2e_sync_step():  # the same through the blocking call, for reference (upload, compute, read back in series)
-        yolo.detect_batch(x_host, use_graph=True, unpack=False)
+        yolo.detect_batch(xu_host, use_graph=True, unpack=False)
 
-    e2e_run(max(a.warmup, 3))
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    t0 = time.perf_counter()
-    e2e_run(a.steps)
-    f1.record()
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    ms_e2e = max(f0.elapsed_time(f1), wall_ms)  # host-side waits count: take the longer clock
+    def timed_e2e(host):
+        e2e_run(max(a.warmup, 3), host)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        t0 = time.perf_counter()
+        e2e_run(a.steps, host)
+        f1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        return max(f0.elapsed_time(f1), wall)  # host-side waits count: take the longer clock
+
+    ms_e2e = timed_e2e(xu_host)
+    ms_e2e_f32 = timed_e2e(x_host)
     for _ in range(3):
         e2e_sync_step()
     barrier()
@@ -343,35 +382,73 @@ def run_b200(a):
     clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
-        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, ms_e2e, ms_e2e_f32], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+        ms, ms_e2e, ms_e2e_f32 = float(t[0]), float(t[1]), float(t[2])
     total_images = a.batch * world * a.steps
     value = total_images / (ms * 1e-3)
     e2e_value = total_images / (ms_e2e * 1e-3)
-    h2d = x_host.numel() * x_host.element_size()
-    d2h = eng.pp.d2h_bytes() * (world if (gather is not None) else 1)
+    h2d = xu_host.numel() * xu_host.element_size()
+    h2d_f32 = x_host.numel() * x_host.element_size()
+    # device->host per step: every rank reads its own wire; rank 0 additionally reads the gathered wires of all ranks
+    d2h = eng.pp.d2h_bytes() * ((2 * world) if (gather is not None) else 1)
 
+    # ---- multi-GPU equivalence (outside the timed regions): rank r's slice of the gathered wire == what ONE GPU
+    # returns for rank r's images -------------------------------------------------------
+    equivalence = None
+    if gather is not None:
+        yolo.detect_batch(x_host, unpack=False)
+        gather.all_gather()
+        parts = gather.read()
+        if rank == 0:
+            same, checked = True, 0
+            for r in range(world):
+                xr = x_host if r == 0 else make_inputs(a, a.batch, 1234 + r).pin_memory()
+                mine = yolo.detect_batch(xr)
+                theirs = eng.pp.unpack_wire(parts[r])
+                for p, q in zip(mine, theirs):
+                    same = same and all(np.array_equal(u, v) for u, v in zip(p, q))
+                checked += 1
+            equivalence = {"ranks_checked": checked, "identical_to_single_gpu": bool(same)}
+        barrier()
+
+    verified, verify_report = (None, None)
+    if rank == 0 and not a.no_verify:
+        verified, verify_report = verify_against_oracle(a, yolo, weights, anchors, x_host, xu_host)
+        if equivalence is not None:
+            verified = bool(verified and equivalence["identical_to_single_gpu"])
+
+    picks = {}
+    for i, v in sorted(eng.pw_choice.items()):
+        picks[eng.net.layers[i].name] = {_lib.PW_TC: "tc", _lib.PW_TS: "ts"}.get(v, str(v))
     out = {
         "metric": METRIC if a.size == 416 else "images/sec at %dx%d" % (a.size, a.size), "value": value, "unit": UNIT,
         "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": "f32", "arith": ARITH, "data": "synthetic",
         "config": {"workload": workload_name(a), "global_batch": a.batch * world, "micro_batch": eng.micro, "lanes": eng.lanes,
-                   "parallelism": "batch-sharded x%d, NCCL all-gather of packed detections" % world if world > 1
+                   "parallelism": "batch-sharded x%d, NCCL all-gather of packed detections (side stream)" % world if world > 1
                    else "single GPU", "weights": "seeded random init (head biases calibrated to ~1% boxes > 0.2)",
                    "score_threshold": SCORE, "iou_threshold": IOU, "detections_per_step_rank0": n_det,
                    "l2": "inputs larger than L2: fp32 batch = %.0f MB and one step moves ~%.1f GB of activations "
                          "through a 126 MB L2, so nothing survives between timed iterations"
-                         % (h2d / 1e6, nd.totals()["bytes"] * a.batch / 1e9)},
+                         % (h2d_f32 / 1e6, nd.totals()["bytes"] * a.batch / 1e9)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / a.steps,
-                "api": "YOLO.detect_stream(pinned host fp32 [B,416,416,3] batches): per step H2D of the batch, graph "
-                       "replay, one D2H of the packed detections; upload of step i+1 overlaps compute of step i",
-                "blocking_call": {"value": total_images / (ms_e2e_sync * 1e-3) , "ms_per_step": ms_e2e_sync / a.steps,
-                                  "api": "YOLO.detect_batch (upload, compute, read back in series)"}},
+                "api": "YOLO.detect_stream(pinned host uint8 [B,%d,%d,3] batches, as an image decoder delivers them; the "
+                       "stem kernel applies 1/255): per step H2D of the batch, graph replay, one D2H of the packed "
+                       "detections (+ all-gather and rank 0's read of every rank's detections when N > 1); upload of "
+                       "step i+1 overlaps compute of step i" % (a.size, a.size),
+                "fp32_upload": {"value": total_images / (ms_e2e_f32 * 1e-3), "ms_per_step": ms_e2e_f32 / a.steps,
+                                "h2d_bytes_per_step": h2d_f32,
+                                "api": "the same with float32 [0,1] host batches (4x the upload bytes)"},
+                "blocking_call": {"value": total_images / (ms_e2e_sync * 1e-3), "ms_per_step": ms_e2e_sync / a.steps,
+                                  "api": "YOLO.detect_batch on the uint8 batch (upload, compute, read back in series)"}},
         "gpu_launches": launches_per_step * a.steps,
         "clocks": clocks,
+        "verified": verified, "verify": verify_report, "multi_gpu_equivalence": equivalence,
+        "pw_kernel_picks": {"tc": sum(1 for v in picks.values() if v == "tc"), "ts": sum(1 for v in picks.values() if v == "ts"),
+                            "per_layer": picks},
     }
 
     if rank == 0 and not a.no_roofline:

@@ -64,41 +64,5 @@ def pack_tc(w, variant=_lib.PW_TC):
     return packed
 
 
-# ---- end-to-end detection comparison with a tie margin -------------------------------------------
-def _iou(a, b):
-    iy0, ix0 = max(a[0], b[0]), max(a[1], b[1])
-    iy1, ix1 = min(a[2], b[2]), min(a[3], b[3])
-    inter = max(iy1 - iy0, 0.0) * max(ix1 - ix0, 0.0)
-    ua = (a[2] - a[0]) * (a[3] - a[1]) + (b[2] - b[0]) * (b[3] - b[1]) - inter
-    return inter / ua if ua > 0 else 0.0
-
-
-def assert_detections_match(got, ref, score_thr, iou_thr, tol=1e-3, box_tol_px=1.0, margin=5e-3):
-    """got / ref: (boxes [n,4], scores [n], classes [n]).  Two fp32 implementations of the network differ
-    by rounding, and yolo_eval is discontinuous (score > thr, IoU > thr), so a detection may legally
-    appear on one side only when it sits within ``margin`` of a decision boundary.  Everything else must
-    pair up one-to-one with the same class, |score diff| <= tol and |box diff| <= box_tol_px.
-    Returns (matched, marginal)."""
-    gb, gs, gc = (np.asarray(v) for v in got)
-    rb, rs, rc = (np.asarray(v) for v in ref)
-    used = np.zeros(len(rs), bool)
-    unmatched = []
-    matched = 0
-    for i in range(len(gs)):
-        cand = [j for j in range(len(rs)) if not used[j] and rc[j] == gc[i] and abs(float(rs[j]) - float(gs[i])) <= tol
-                and np.abs(rb[j].astype(np.float64) - gb[i].astype(np.float64)).max() <= box_tol_px]
-        if cand:
-            used[cand[0]] = True
-            matched += 1
-        else:
-            unmatched.append(("got", gb[i], float(gs[i]), int(gc[i])))
-    unmatched += [("ref", rb[j], float(rs[j]), int(rc[j])) for j in range(len(rs)) if not used[j]]
-    for side, box, score, cls in unmatched:
-        near_thr = abs(score - score_thr) <= margin
-        ob, os_, oc = (gb, gs, gc) if side == "ref" else (rb, rs, rc)  # the side that dropped it
-        near_iou = any(oc[k] == cls and os_[k] >= score - tol and abs(_iou(box.astype(np.float64), ob[k].astype(np.float64))
-                                                                     - iou_thr) <= 10 * margin for k in range(len(os_)))
-        capped = (np.sum(gc == cls) >= 20) or (np.sum(rc == cls) >= 20)  # max_boxes cut shifts the tail
-        assert near_thr or near_iou or capped, "unexplained %s-only detection: class %d score %.5f box %s" % (
-            side, cls, score, box)
-    return matched, len(unmatched)
+# ---- end-to-end detection comparison with a tie margin (shared with bench.py's verify leg) ----------
+from oracle.verify import assert_detections_match  # noqa: E402,F401

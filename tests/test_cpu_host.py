@@ -130,6 +130,19 @@ def _gather_worker(rank, world, port, words, q):
         g.all_gather()
         ok = ok and all(np.array_equal(p, np.arange(words, dtype=np.int32) + 1000 * r + 7)
                         for r, p in enumerate(g.read()))
+        # pipelined form: results are picked up one step late; the double buffers keep step i intact while i+1 runs
+        t_prev, seen = None, []
+        for step in range(4):
+            wire.copy_(torch.arange(words, dtype=torch.int32) + 1000 * rank + 31 * step)
+            t = g.gather_async()
+            if t_prev is not None:
+                seen.append([p.copy() for p in g.wait(t_prev)])
+            t_prev = t
+        seen.append([p.copy() for p in g.wait(t_prev)])
+        g.join()
+        for step, parts in enumerate(seen):
+            ok = ok and all(np.array_equal(p, np.arange(words, dtype=np.int32) + 1000 * r + 31 * step)
+                            for r, p in enumerate(parts))
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()

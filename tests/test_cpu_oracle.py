@@ -149,3 +149,44 @@ def test_loss_oracle_properties():
     b2 = torch.tensor([[0.6, 0.6, 0.9, 0.9]], dtype=torch.float64)
     enclose, union = 0.8 * 0.8, 0.16 + 0.09
     assert abs(float(oloss.do_giou_calculate(b, b2)) + (enclose - union) / enclose) < 1e-12
+
+
+# ---- EfficientNet-B3 (SE blocks, 5x5 depthwise, Swish): the shipped COCO checkpoint ---------------------------------
+def test_b3_checkpoint_realigns_and_oracle_reproduces_golden(gold):
+    """reference code/checkpoints/efficientnetb3_416_coco.h5 as stored (tests/golden/b3_coco_weights.npz keeps the
+    checkpoint's own Keras names).  The reference builds the EfficientNet backbone twice (code/yolo3/model.py:205-217),
+    which shifts Keras' auto-numbering: 141 of the 603 names differ from a single graph build, so loading goes through
+    ``weights.align_weights`` (per layer kind, in creation order).  Pins: every array is consumed exactly once, shapes
+    and the parameter count (8 868 749) match, and the oracle on demo image 0 reproduces the committed logits and the
+    confident COCO detections (person / bicycle / car) of tests/golden/demo_detections_b3.json."""
+    from yoloret_b200.netdef import NetDef
+    from yoloret_b200.weights import align_weights
+    z = np.load(os.path.join(GOLD, "b3_coco_weights.npz"))
+    have = {k.replace("__", "/"): z[k] for k in z.files}
+    spec = NetDef("efficientnetb3", 80, (416, 416)).weight_shapes
+    assert dict(spec) == dict(ograph.weight_spec("efficientnetb3", 80))   # product and oracle agree on the graph
+    assert len(have) == len(spec) == 603 and sum(1 for k in spec if k not in have) == 141
+    w = align_weights(have, spec)
+    assert list(w) == list(spec) and sum(int(v.size) for v in w.values()) == 8868749
+    used = {id(v) for v in w.values()}
+    assert len(used) == 603 and used == {id(v) for v in have.values()}    # a bijection: nothing reused or dropped
+    # names that exist on both sides but hold DIFFERENT layers must have been remapped, not taken by name
+    assert w["batch_normalization_78/gamma"] is have["batch_normalization_156/gamma"]
+    with pytest.raises(KeyError):
+        align_weights({k: v for k, v in have.items() if k != "conv2d_10/kernel"}, spec)
+
+    g = np.load(os.path.join(GOLD, "demo_golden_b3.npz"))
+    img = olb.decode_image_u8(gold["jpeg_0"].tobytes())
+    x = olb.letterbox_image(olb.u8_to_float(img), (416, 416))
+    ys = [y.numpy() for y in ograph.forward(w, x[None], "efficientnetb3", 80)]
+    for s in range(3):
+        np.testing.assert_allclose(ys[s], g["y%d_0" % (s + 1)], atol=5e-5)
+    b, sc, cl = opp.yolo_eval(ys, g["anchors"], 3, 80, img.shape[:2], score_threshold=0.3, iou_threshold=0.5)
+    np.testing.assert_array_equal(cl, g["det_classes_0"])
+    np.testing.assert_allclose(sc, g["det_scores_0"], atol=1e-5)
+    assert np.abs(b.astype(np.int64) - g["det_boxes_i_0"]).max() <= 1
+    names = [str(c) for c in g["classes"]]
+    best = {}
+    for c, s_ in zip(cl, sc):
+        best[names[c]] = max(best.get(names[c], 0.0), float(s_))
+    assert best["person"] > 0.99 and best["bicycle"] > 0.8 and best["car"] > 0.9

@@ -7,6 +7,7 @@ fails, this module raises.  (``yoloret_b200.build.build_library`` /
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -115,3 +116,18 @@ def check(rc: int, what: str = ""):
     if rc != 0:
         raise YrError("%s failed (status %d): %s" % (what or "yoloret_b200 call", rc,
                                                      lib().yr_last_error().decode(errors="replace")))
+
+
+def on_device(fn):
+    """Method decorator: runs ``fn`` with ``self.device`` as the current CUDA device.  Function attributes, the SM
+    count and streams are per device, so an Engine / PostProcess built for ``cuda:1`` must make that device current
+    around its library calls even when the caller's current device is ``cuda:0``."""
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        import torch
+        dev = getattr(self, "device", None)
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(self, *args, **kwargs)
+    return wrapper

@@ -280,7 +280,8 @@ static int launch_dw_tma_cfg(const yr_op& op, const dwt::Plan& pl, const CUtenso
     p.pad_l = op.pad_l;
     p.stage_floats = pl.stage_floats;
     const size_t smem = (size_t)2 * pl.stage_floats * 4 + 128;
-    static bool attr_set = false;
+    static DeviceOnce attr_once;  // function attributes are per device
+    bool& attr_set = attr_once.cur();
     if (!attr_set) {
         if (cudaFuncSetAttribute(dwt::dw_tma_kernel<S, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  2 * dwt::STAGE_LIMIT + 128) != cudaSuccess) {

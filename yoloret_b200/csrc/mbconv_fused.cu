@@ -532,7 +532,8 @@ int launch_mbconv(const yr_op& op, cudaStream_t s) {
         set_error("mbconv: cuTensorMapEncodeTiled failed (%d)", (int)cr);
         return YR_ERR_CUDA;
     }
-    static bool attr_set = false;
+    static DeviceOnce attr_once;  // function attributes are per device
+    bool& attr_set = attr_once.cur();
     if (!attr_set) {
         if (cudaFuncSetAttribute(mbconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
             set_error("mbconv: cannot raise the dynamic shared memory limit");

@@ -281,7 +281,8 @@ static bool launch_stem_v3(const yr_op& op, cudaStream_t s) {
     row_floats = (row_floats + 3) & ~3;
     const size_t smem = ((size_t)((27 * op.N + 3) & ~3) + (size_t)(2 * TH + 1) * row_floats) * sizeof(float);
     if (smem > 160 * 1024) return false;
-    static bool attr_set = false;
+    static DeviceOnce attr_once;  // function attributes are per device
+    bool& attr_set = attr_once.cur();
     if (!attr_set) {
         cudaFuncSetAttribute(stem_kernel_v3<ACT, U8, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         attr_set = true;
@@ -543,7 +544,8 @@ int launch_rfcr(const yr_op& op, cudaStream_t s) {
     const int W = op.Wo;
     const size_t smem = ((size_t)(K1 + K2 + K3 + K4) * N + (size_t)RFCR_ROWS * W * K4) * sizeof(float);
     YR_CHECK_ARG(smem <= 200 * 1024, "rfcr: taps / row too large for shared memory (%zu bytes)", smem);
-    static bool attr_set = false;
+    static DeviceOnce attr_once;  // function attributes are per device
+    bool& attr_set = attr_once.cur();
     if (!attr_set) {
         cudaFuncSetAttribute(rfcr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;

@@ -522,7 +522,8 @@ extern "C" int yr_decode_filter(const float* const feats[3], const float* image_
     }
     const size_t smem = (size_t)DEC_BOXES * p->num_classes * sizeof(float);
     if (smem > 48 * 1024) {
-        static bool attr = false;
+        static DeviceOnce attr_once;  // function attributes are per device
+        bool& attr = attr_once.cur();
         if (!attr) {
             cudaFuncSetAttribute(decode_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             attr = true;

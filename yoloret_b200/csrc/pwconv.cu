@@ -166,7 +166,8 @@ static int launch_cfg(const yr_op& op, cudaStream_t s) {
     const int M = op.B * op.H * op.W;
     const size_t smem = (size_t)(2 * BM * (PW_BK + PW_APAD) + 2 * PW_BK * BN) * sizeof(float);
     auto kern = pw_simt_kernel<TX, TY, GM, GN, ACT, HAS_RES, HAS_SCALE>;
-    static bool attr_set = false;
+    static DeviceOnce attr_once;  // function attributes are per device
+    bool& attr_set = attr_once.cur();
     if (!attr_set) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;

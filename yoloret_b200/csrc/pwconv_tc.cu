@@ -610,7 +610,8 @@ int launch_pw_tc(const yr_op& op, cudaStream_t s) {
     const int grid = (p.total_items + p.items_per_cta - 1) / p.items_per_cta;
     // instruction descriptor: D=F32, A=B=TF32, both K-major, N=BN, M=128
     p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(t.BN >> 3) << 17) | ((uint32_t)(tc::BM >> 4) << 24);
-    static bool attr_set = false;
+    static DeviceOnce attr_once;  // function attributes are per device
+    bool& attr_set = attr_once.cur();
     if (!attr_set) {
         if (cudaFuncSetAttribute(tc::pw_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT) !=
                 cudaSuccess ||

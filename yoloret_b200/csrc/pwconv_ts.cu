@@ -601,7 +601,8 @@ int launch_pw_ts(const yr_op& op, cudaStream_t s) {
     p.a_col0 = t.a_col0;
     p.epi_group_bytes = t.epi_group_bytes;
     p.total_items = p.n_tiles * p.m_tiles;
-    static bool attr_set = false;
+    static DeviceOnce attr_once;  // function attributes are per device
+    bool& attr_set = attr_once.cur();
     if (!attr_set) {
         if (cudaFuncSetAttribute(ts::pw_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM_LIMIT) !=
                 cudaSuccess ||

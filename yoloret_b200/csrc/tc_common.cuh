@@ -158,11 +158,12 @@ inline CUtensorMapL2promotion l2_promotion() {
     return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : (v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
 }
 
-inline int num_sms() {
-    static int n = 0;
+inline int num_sms() {  // of the CURRENT device (cached per device)
+    static int cache[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& n = cache[dev & 63];
     if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     }
     return n;

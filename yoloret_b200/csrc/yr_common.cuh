@@ -29,6 +29,17 @@ void set_error(const char* fmt, ...);
 
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// A "done once" flag PER DEVICE: function attributes (the dynamic shared-memory limit) and the SM count belong to
+// a device, so a process that drives several GPUs must set / query them once per device, not once per process.
+struct DeviceOnce {
+    bool done[64] = {};
+    bool& cur() {
+        int d = 0;
+        cudaGetDevice(&d);
+        return done[d & 63];
+    }
+};
+
 // Activations of the graph: ReLU6 (tf.keras.layers.ReLU(6.)) and Swish
 // (reference code/yolo3/efficientnet.py:327-331: x * sigmoid(x)).
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }

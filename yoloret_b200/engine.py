@@ -61,12 +61,28 @@ class Engine:
                  weights: Dict[str, np.ndarray], anchors: np.ndarray, micro_batch: Optional[int] = None,
                  num_scales: int = 3, max_boxes: int = 20, cand_cap: Optional[int] = None,
                  device: Optional[torch.device] = None, pw_variant: int = _lib.PW_AUTO, input_u8: bool = False,
-                 fuse_se: bool = True, fuse_mbconv: bool = False, lanes: int = 1, autotune: bool = True, fuse_up2: bool = True):
+                 fuse_se: bool = True, fuse_mbconv: bool = False, lanes: int = 1, autotune: bool = True, fuse_up2: bool = True,
+                 num_anchors: int = 3):
         if not torch.cuda.is_available():
             raise _lib.YrError("yoloret_b200.Engine needs a CUDA device (no CPU fallback exists)")
         self.lib = _lib.lib()
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
-        self.net = NetDef(model_name, num_classes, input_hw)
+        if self.device.type != "cuda":
+            raise _lib.YrError("yoloret_b200.Engine needs a CUDA device, got %s" % (self.device,))
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.device(self.device):  # allocations, attribute caches and the autotuner run on that GPU
+            self._init(model_name, num_classes, input_hw, batch, weights, anchors, micro_batch, num_scales, max_boxes,
+                       cand_cap, pw_variant, input_u8, fuse_se, fuse_mbconv, lanes, autotune, fuse_up2, num_anchors)
+
+    def _init(self, model_name, num_classes, input_hw, batch, weights, anchors, micro_batch, num_scales, max_boxes,
+              cand_cap, pw_variant, input_u8, fuse_se, fuse_mbconv, lanes, autotune, fuse_up2, num_anchors):
+        # the reference derives anchors per scale as num_anchors // num_scales (code/yolo.py:214-216); decode, the head
+        # width and the y_true layout of this engine are written for 3 per scale (every shipped anchor file: 9 / 3)
+        if int(num_anchors) != 3:
+            raise ValueError("this engine supports 3 anchors per scale (got %d): pass 9 anchors with num_scales=3"
+                             % int(num_anchors))
+        self.net = NetDef(model_name, num_classes, input_hw, int(num_anchors))
         self.model_name, self.num_classes, self.input_hw = model_name, num_classes, tuple(input_hw)
         self.batch = int(batch)
         # lanes > 1: the micro-batches of a step run concurrently on that many CUDA streams (fork/join inside the
@@ -128,10 +144,11 @@ class Engine:
                         self.micro, b.H, b.W, b.ld)
                 self.buf_t[b.name] = self.lane_buf_t[0][b.name]
         self.arena_bytes = total * 4 * self.lanes
-        in_dtype = torch.uint8 if self.input_u8 else torch.float32
-        # two input slots: slot 1 exists so a streaming caller can upload batch i+1 while batch i computes
-        self.inputs = [torch.zeros(self.batch, self.input_hw[0], self.input_hw[1], 3, dtype=in_dtype, device=dev)]
-        self.input = self.inputs[0]
+        # input slots, keyed (slot, is_u8): float32 images in [0,1] or raw uint8 images (the stem scales by 1/255 like
+        # tf.io.decode_image(dtype=float32), reference code/yolo.py:106); a second slot lets a streaming caller upload
+        # batch i+1 while batch i computes.  ``self.input`` is slot 0 of the engine's default dtype.
+        self.inputs: Dict[Tuple[int, bool], torch.Tensor] = {}
+        self.input = self.input_slot(0)
         grids = [(v.H, v.W) for v in net.outputs]
         self.pp = PostProcess(self.batch, grids, self.num_classes, self.anchors, self.num_scales, self.max_boxes,
                               device=dev, cand_cap=self.cand_cap_arg)
@@ -316,28 +333,43 @@ class Engine:
         self._plans.clear()  # plans were built with the provisional variants
 
     # ---- plan ---------------------------------------------------------------------
-    def input_slot(self, slot: int) -> torch.Tensor:
-        while len(self.inputs) <= slot:
-            self.inputs.append(torch.zeros_like(self.inputs[0]))
-        return self.inputs[slot]
+    def input_slot(self, slot: int = 0, u8: Optional[bool] = None) -> torch.Tensor:
+        """Device input buffer ``slot`` for uint8 (``u8=True``) or float32 batches (default: the engine's dtype)."""
+        key = (int(slot), self.input_u8 if u8 is None else bool(u8))
+        t = self.inputs.get(key)
+        if t is None:
+            t = self.inputs[key] = torch.zeros(self.batch, self.input_hw[0], self.input_hw[1], 3,
+                                               dtype=torch.uint8 if key[1] else torch.float32, device=self.device)
+        return t
 
-    def _ptr(self, v: View, chunk0: int, slot: int = 0, lane: int = 0) -> int:
+    def slot_for(self, images: torch.Tensor, slot: int = 0) -> Tuple[torch.Tensor, bool]:
+        """Validates a [B,H,W,3] uint8 / float32 batch and returns (its device input buffer, is_u8)."""
+        want = (self.batch, self.input_hw[0], self.input_hw[1], 3)
+        if tuple(images.shape) != want or images.dtype not in (torch.uint8, torch.float32):
+            raise ValueError("expected %s uint8 or float32, got %s %s" % (want, tuple(images.shape), images.dtype))
+        u8 = images.dtype == torch.uint8
+        return self.input_slot(slot, u8), u8
+
+    def _ptr(self, v: View, chunk0: int, slot: int = 0, lane: int = 0, u8: Optional[bool] = None) -> int:
         """Device address of a view for the micro-batch starting at image ``chunk0`` (arena of ``lane``)."""
-        t = self.input_slot(slot) if v.buf.name == "input" else self.lane_buf_t[lane][v.buf.name]
+        t = self.input_slot(slot, u8) if v.buf.name == "input" else self.lane_buf_t[lane][v.buf.name]
         base = t.data_ptr() + v.off * t.element_size()
         if v.buf.full_batch:
             base += chunk0 * v.buf.H * v.buf.W * v.buf.ld * t.element_size()
         return base
 
-    def build_plan(self, chunk0: int, nb: int, slot: int = 0, lane: int = 0):
-        """yr_op array for images [chunk0, chunk0+nb) reading input slot ``slot``, activations in arena ``lane``."""
-        key = (chunk0, nb, slot, lane)
+    @_lib.on_device
+    def build_plan(self, chunk0: int, nb: int, slot: int = 0, lane: int = 0, u8: Optional[bool] = None):
+        """yr_op array for images [chunk0, chunk0+nb) reading input slot ``slot`` (uint8 or float32 flavour),
+        activations in arena ``lane``."""
+        u8 = self.input_u8 if u8 is None else bool(u8)
+        key = (chunk0, nb, slot, lane, u8)
         if key in self._plans:
             return self._plans[key]
         _ptr0 = self._ptr
 
         def _ptr(v, c0, sl=0):
-            return _ptr0(v, c0, sl, lane)
+            return _ptr0(v, c0, sl, lane, u8)
         ops = (YrOp * len(self.net.layers))()
         gate_ptr: Dict[int, int] = {}
         meta = []   # per emitted op: (kind, name, algorithmic bytes / image, flops / image, layer index)
@@ -383,7 +415,7 @@ class Engine:
             if L.kind == "stem":
                 o.kind = _lib.OP_STEM
                 o.C = 3
-                o.in_is_u8 = 1 if self.input_u8 else 0
+                o.in_is_u8 = 1 if u8 else 0
             elif L.kind == "pw":
                 o.kind = _lib.OP_PW
                 o.variant = self._pw_variant_of(i)
@@ -439,14 +471,15 @@ class Engine:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def run_network(self, slot: int = 0):
+    @_lib.on_device
+    def run_network(self, slot: int = 0, u8: Optional[bool] = None):
         """yolov3_body forward over input slot ``slot`` -> y buffers, micro-batch by micro-batch."""
         chunks = [(c0, min(self.micro, self.batch - c0)) for c0 in range(0, self.batch, self.micro)]
         n = 0
         if self.lanes == 1 or len(chunks) == 1:
             st = self._stream()
             for c0, nb in chunks:
-                ops, cnt = self.build_plan(c0, nb, slot)
+                ops, cnt = self.build_plan(c0, nb, slot, 0, u8)
                 _lib.check(self.lib.yr_run_ops(ops, cnt, st), "yr_run_ops")
                 n += cnt
             return n
@@ -462,7 +495,7 @@ class Engine:
             ls.wait_event(fork)
             for j in range(lane, len(chunks), self.lanes):
                 c0, nb = chunks[j]
-                ops, cnt = self.build_plan(c0, nb, slot, lane)
+                ops, cnt = self.build_plan(c0, nb, slot, lane, u8)
                 _lib.check(self.lib.yr_run_ops(ops, cnt, ls.cuda_stream), "yr_run_ops")
                 n += cnt
             done = torch.cuda.Event()
@@ -480,33 +513,39 @@ class Engine:
             outs.append(t.as_strided((self.batch, v.H, v.W, 3, E), (v.H * v.W * ld, v.W * ld, ld, E, 1)))
         return outs
 
+    @_lib.on_device
     def run_postprocess(self, score_threshold: float, iou_threshold: float) -> int:
         """yolo_eval (model.py:431-491) on the y buffers."""
         ptrs = [self.buf_t[v.buf.name].data_ptr() for v in self.net.outputs[:self.num_scales]]
         ld = [v.buf.ld for v in self.net.outputs[:self.num_scales]]
         return self.pp.run(ptrs, ld, score_threshold, iou_threshold, self._stream())
 
-    def step(self, score_threshold: float, iou_threshold: float, slot: int = 0) -> int:
+    @_lib.on_device
+    def step(self, score_threshold: float, iou_threshold: float, slot: int = 0, u8: Optional[bool] = None) -> int:
         """One full pass: network + post-process on whatever is in the input slot. Returns #kernel launches."""
-        n = self.run_network(slot)
+        n = self.run_network(slot, u8)
         self.run_postprocess(score_threshold, iou_threshold)
         self.launches_per_forward = n + 3
         return n + 3
 
-    def capture(self, score_threshold: float, iou_threshold: float, slot: int = 0):
+    @_lib.on_device
+    def capture(self, score_threshold: float, iou_threshold: float, slot: int = 0, u8: Optional[bool] = None):
         """Captures step() into a CUDA graph (launch-bound at small batch: ~90 kernels / micro-batch)."""
-        self.step(score_threshold, iou_threshold, slot)  # warm-up: sets func attributes outside capture
+        self.input_slot(slot, u8)
+        self.step(score_threshold, iou_threshold, slot, u8)  # warm-up: sets func attributes outside capture
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self.step(score_threshold, iou_threshold, slot)
+            self.step(score_threshold, iou_threshold, slot, u8)
         self._graph = g
         return g
 
+    @_lib.on_device
     def results(self, with_float_boxes: bool = False):
         return self.pp.results(with_float_boxes)
 
     # ---- per-layer timing (bench.py's roofline leg) ------------------------------------------
+    @_lib.on_device
     def profile_layers(self, score_threshold: float, iou_threshold: float, reps: int = 3):
         """Times every launch of one full step with CUDA events on the launching stream, inside the
         real pipeline order (so each layer sees the cache state it sees in production).  A spin

@@ -29,7 +29,16 @@ def shard_range(batch: int, world: int, rank: int) -> Tuple[int, int]:
 class DetectionGather:
     """All-gathers equal-sized per-rank detection wires.  ``wire``: the rank's flat int32
     tensor (``PostProcess.wire``); on CUDA the collective is NCCL over NVLink, on CPU (tests)
-    gloo."""
+    gloo.
+
+    Two ways to drive it:
+      * ``all_gather()`` [+ ``read()``]: the collective on the caller's stream, then a blocking device->host
+        read - simple, serialises with the next step.
+      * ``gather_async()`` + ``wait(ticket)``: the pipelined form.  The wire is snapshotted into a staging buffer
+        (the only thing the compute stream waits for, ~2.5 MB device-to-device), then the all-gather and the
+        device->host copy of the gathered buffer run on a side stream and overlap the next step's compute; the
+        caller picks the result up one step later.  Device and pinned host buffers are double-buffered, so step
+        i+1 never overwrites what step i's reader still holds."""
 
     def __init__(self, pp_or_wire, world: int, rank: int, group=None):
         self.wire = pp_or_wire.wire if hasattr(pp_or_wire, "wire") else pp_or_wire
@@ -37,24 +46,75 @@ class DetectionGather:
             raise ValueError("wire must be a flat int32 tensor")
         self.world, self.rank, self.group = world, rank, group
         self.words = self.wire.numel()
-        self.gathered = torch.zeros(world * self.words, dtype=torch.int32, device=self.wire.device)
-        self.host = torch.zeros(world * self.words, dtype=torch.int32)
-        if self.wire.is_cuda:
-            self.host = self.host.pin_memory()
+        dev = self.wire.device
+        self._gathered = [torch.zeros(world * self.words, dtype=torch.int32, device=dev) for _ in range(2)]
+        self._host = [torch.zeros(world * self.words, dtype=torch.int32) for _ in range(2)]
+        self.cuda = self.wire.is_cuda
+        if self.cuda:
+            self._host = [h.pin_memory() for h in self._host]
+            self._stage = torch.zeros_like(self.wire)
+            self._side = torch.cuda.Stream(dev)
+            self._staged = torch.cuda.Event()
+            self._landed = [torch.cuda.Event(), torch.cuda.Event()]
+        self._n = 0
+        self.gathered = self._gathered[0]
+        self.host = self._host[0]
+
+    def _collective(self, dst: torch.Tensor, src: torch.Tensor):
+        if self.cuda:
+            dist.all_gather_into_tensor(dst, src, group=self.group)
+        else:
+            dist.all_gather(list(dst.split(self.words)), src, group=self.group)
 
     def all_gather(self) -> torch.Tensor:
-        if self.wire.is_cuda:
-            dist.all_gather_into_tensor(self.gathered, self.wire, group=self.group)
-        else:
-            dist.all_gather(list(self.gathered.split(self.words)), self.wire, group=self.group)
+        """The collective on the current stream; returns the gathered device tensor [world * words]."""
+        self.gathered = self._gathered[self._n & 1]
+        self._n += 1
+        self._collective(self.gathered, self.wire)
         return self.gathered
 
     def read(self) -> List[np.ndarray]:
-        """Device->host copy of the gathered wires; one numpy view per rank, rank order = batch order."""
+        """Blocking device->host copy of the last ``all_gather``; one numpy view per rank, rank order = batch order."""
         self.host.copy_(self.gathered, non_blocking=True)
-        if self.wire.is_cuda:
+        if self.cuda:
             torch.cuda.current_stream(self.wire.device).synchronize()
         return list(self.host.numpy().reshape(self.world, self.words))
+
+    def gather_async(self, read: bool = True) -> int:
+        """Pipelined form: snapshot the wire, then all-gather (+ device->host copy when ``read``) on a side stream.
+        Returns a ticket for ``wait``.  The caller's stream only waits for the snapshot."""
+        k = self._n & 1
+        self._n += 1
+        self.gathered = self._gathered[k]
+        if not self.cuda:
+            self._collective(self.gathered, self.wire)
+            if read:
+                self._host[k].copy_(self.gathered)
+            return k
+        main = torch.cuda.current_stream(self.wire.device)
+        side = self._side
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self._stage.copy_(self.wire, non_blocking=True)
+            self._staged.record(side)
+            self._collective(self.gathered, self._stage)
+            if read:
+                self._host[k].copy_(self.gathered, non_blocking=True)
+            self._landed[k].record(side)
+        main.wait_event(self._staged)  # the next step may overwrite the wire once the snapshot exists
+        return k
+
+    def wait(self, ticket: int) -> List[np.ndarray]:
+        """Blocks the HOST until the gather (and read) of ``ticket`` has landed; numpy views per rank."""
+        if self.cuda:
+            self._landed[ticket].synchronize()
+        self.host = self._host[ticket]
+        return list(self.host.numpy().reshape(self.world, self.words))
+
+    def join(self):
+        """Makes the current stream wait for every side-stream gather issued so far (device-side join)."""
+        if self.cuda:
+            torch.cuda.current_stream(self.wire.device).wait_stream(self._side)
 
 
 class GradBucket:

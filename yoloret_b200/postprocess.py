@@ -24,6 +24,8 @@ class PostProcess:
             raise _lib.YrError("yoloret_b200 post-process needs a CUDA device (no CPU fallback exists)")
         self.lib = _lib.lib()
         dev = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        if dev.type == "cuda" and dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
         self.device = dev
         self.batch, self.num_classes, self.num_scales, self.max_boxes = batch, num_classes, num_scales, max_boxes
         self.grids = [tuple(g) for g in grids[:num_scales]]
@@ -67,6 +69,7 @@ class PostProcess:
         self.workspace_bytes = sum(t.numel() * t.element_size() for t in (
             self.boxes, self.cand_score, self.cand_index, self.cand_count, self.det, self.det_count, self.flat))
 
+    @_lib.on_device
     def set_image_shapes(self, shapes):
         """shapes: [B,2] (h,w) of the original images (yolo_eval's image_shape), or one (h,w) for all."""
         a = np.asarray(shapes, dtype=np.float32)
@@ -93,6 +96,7 @@ class PostProcess:
         p.cand_cap = self.cand_cap
         return p
 
+    @_lib.on_device
     def run(self, feat_ptrs: Sequence[int], ld: Sequence[int], score_threshold: float, iou_threshold: float,
             stream: Optional[int] = None, events=None) -> int:
         """decode+filter -> class-wise NMS -> pack.  Returns the number of kernels launched."""
@@ -127,6 +131,7 @@ class PostProcess:
     def d2h_bytes(self, with_float_boxes: bool = False) -> int:
         return (self.flat.numel() if with_float_boxes else self.wire_words) * 4
 
+    @_lib.on_device
     def enqueue_read(self, slot: int = 0) -> torch.Tensor:
         """Asynchronous device->host copy of the wire words on the current stream into pinned landing
         buffer ``slot`` (0/1); the caller synchronises (event) before touching the returned tensor."""
@@ -136,6 +141,7 @@ class PostProcess:
         dst.copy_(self.wire, non_blocking=True)
         return dst
 
+    @_lib.on_device
     def read_wire(self, with_float_boxes: bool = False) -> np.ndarray:
         """ONE device->host copy of the wire buffer into pinned host memory (synchronises the stream)."""
         n = self.flat.numel() if with_float_boxes else self.wire_words

@@ -25,8 +25,13 @@ def load_checkpoint(path: str, weight_shapes: Mapping[str, Tuple[int, ...]]) -> 
     shifts Keras' auto-numbering), weights are matched per kind in creation order, like
     Keras' topological ``load_weights`` does.
     """
-    f = H5File(path)
-    have = f.weights()
+    return align_weights(H5File(path).weights(), weight_shapes, path)
+
+
+def align_weights(have: Mapping[str, np.ndarray], weight_shapes: Mapping[str, Tuple[int, ...]],
+                  path: str = "<arrays>") -> Dict[str, np.ndarray]:
+    """``have``: the arrays of a checkpoint by their stored Keras names -> ``{name: array}`` for ``weight_shapes``
+    (by name when every name and shape lines up, else per layer kind in creation order; see ``load_checkpoint``)."""
     if all(k in have and tuple(have[k].shape) == tuple(s) for k, s in weight_shapes.items()):
         return {k: have[k] for k in weight_shapes}
 
@@ -36,6 +41,7 @@ def load_checkpoint(path: str, weight_shapes: Mapping[str, Tuple[int, ...]]) -> 
         return (base, int(num)) if num.isdigit() and base else (layer, 0)
 
     out: Dict[str, np.ndarray] = {}
+    consumed = set()
     by_base_have: Dict[str, list] = {}
     for n in have:
         b, i = key(n)
@@ -68,10 +74,19 @@ def load_checkpoint(path: str, weight_shapes: Mapping[str, Tuple[int, ...]]) -> 
         b, i = key(n)
         j = remap[(b, i)]
         hn = "%s/%s" % (b if j == 0 else "%s_%d" % (b, j), n.split("/")[1])
+        if hn not in have:
+            raise KeyError("cannot align %s: checkpoint %s has no %s" % (n, path, hn))
         arr = have[hn]
         if tuple(arr.shape) != tuple(shape):
             raise ValueError("weight %s <- %s: shape %s, expected %s" % (n, hn, arr.shape, shape))
         out[n] = arr
+        consumed.add(hn)
+    # order-based matching is only trustworthy as a bijection: a checkpoint array left over (or used twice) means a
+    # layer was skipped and everything behind it may be shifted onto same-shaped neighbours
+    left = sorted(set(have) - consumed)
+    if left or len(consumed) != len(out):
+        raise KeyError("cannot align checkpoint %s with the graph: %d arrays unmatched (e.g. %s)"
+                       % (path, len(left), ", ".join(left[:4])))
     return out
 
 

@@ -53,7 +53,7 @@ class YoloModel:
     def parse_image(self, image: bytes):
         """reference code/yolo.py:105-112: decode (host, PIL) -> letterbox on the GPU."""
         from PIL import Image
-        arr = np.asarray(Image.open(io.BytesIO(image)).convert("RGB"), dtype=np.uint8)
+        arr = np.array(Image.open(io.BytesIO(image)).convert("RGB"), dtype=np.uint8)
         dev_img = torch.from_numpy(arr).to(self.engine.device, non_blocking=True)
         return arr.shape[:2], letterbox_image(dev_img, self.input_shapes)
 
@@ -63,12 +63,10 @@ class YoloModel:
             raise ValueError("YoloModel.__call__ is the reference's batch-1 path; use YOLO.detect_batch")
         e = self.engine
         shape, lb = self.parse_image(input[0])
-        if e.input_u8:
-            raise ValueError("engine built for uint8 batches; detect_image needs a float32 engine")
-        e.input[0].copy_(lb)
+        e.input_slot(0, False)[0].copy_(lb)  # the letterboxed image is float32 in [0,1] (reference code/yolo.py:105-112)
         e.pp.set_image_shapes(shape)
         if self._graph is None:  # the ~90 launches of a step replay as one CUDA graph from the second image on
-            self._graph = e.capture(self.score, self.nms)
+            self._graph = e.capture(self.score, self.nms, 0, False)
         self._graph.replay()
         boxes, scores, classes = e.results()[0]
         if self.with_classes:
@@ -159,34 +157,39 @@ class YOLO(object):
     # ---- batched extension -----------------------------------------------------------
     def detect_batch(self, images, image_shapes=None, use_graph: bool = True, unpack: bool = True):
         """``images``: [B,H,W,3] tensor already at the network input size - uint8 (scaled by 1/255
-        on the GPU like tf.io.decode_image(dtype=float32)) or float32 in [0,1] - on the host
+        on the GPU like tf.io.decode_image(dtype=float32)) or float32 in [0,1], either accepted by any engine - on the host
         (pinned memory recommended) or on the device.  ``image_shapes``: [B,2] original (h,w)
         per image (default: the input size).  Returns per-image (boxes, scores, classes) numpy
         arrays (``unpack=False``: the padded form ``(counts [B], boxes [B,20*C,4] int32, scores
         [B,20*C], classes [B,20*C])`` as views of the pinned host buffer, valid until the next call);
         includes the host->device copy of the batch and ONE device->host read of the results."""
         e = self.engine
-        if tuple(images.shape) != tuple(e.input.shape) or images.dtype != e.input.dtype:
-            raise ValueError("expected %s %s, got %s %s" % (tuple(e.input.shape), e.input.dtype,
-                                                            tuple(images.shape), images.dtype))
-        e.input.copy_(images, non_blocking=True)
+        dst, u8 = e.slot_for(images)
+        dst.copy_(images, non_blocking=True)
         e.pp.set_image_shapes(image_shapes if image_shapes is not None else self.input_shape)
         if use_graph:
-            if self._graph is None:
-                self._graph = e.capture(self.score, self.nms)
-            self._graph.replay()
+            if getattr(self, "_batch_graphs", None) is None:
+                self._batch_graphs = {}
+            if u8 not in self._batch_graphs:
+                self._batch_graphs[u8] = e.capture(self.score, self.nms, 0, u8)
+            self._batch_graphs[u8].replay()
         else:
-            e.step(self.score, self.nms)
+            e.step(self.score, self.nms, 0, u8)
         if unpack:
             return e.results()
         return e.pp.padded_views(e.pp.read_wire())
 
-    def detect_stream(self, batches, image_shapes=None, unpack: bool = True):
-        """Pipelined ``detect_batch`` over an iterable of host batches (pinned memory recommended): yields one
-        result per batch, in order.  The host->device upload of batch i+1 runs on a copy stream into a
+    def detect_stream(self, batches, image_shapes=None, unpack: bool = True, gather=None, gather_read: bool = True):
+        """Pipelined ``detect_batch`` over an iterable of host batches (pinned memory recommended; uint8 or float32):
+        yields one result per batch, in order.  The host->device upload of batch i+1 runs on a copy stream into a
         second input slot while batch i computes, and each batch's detections come back with ONE
         device->host copy, so in steady state a step costs max(compute, PCIe) instead of their sum.
-        Every batch is still uploaded, computed and read back; nothing is cached between batches."""
+        Every batch is still uploaded, computed and read back; nothing is cached between batches.
+
+        Multi-GPU: pass ``gather`` (a ``parallel.DetectionGather`` over this engine's wire).  Every step then also
+        all-gathers the ranks' detection wires on a side stream, overlapped with the next step's compute, and the
+        generator yields ``(local_result, parts)`` with ``parts`` = one wire (numpy int32 view) per rank in rank =
+        batch order (``None`` when ``gather_read`` is False: the gathered buffer stays on the device)."""
         e = self.engine
         dev = e.device
         main = torch.cuda.current_stream(dev)
@@ -194,24 +197,35 @@ class YOLO(object):
             self._copy_stream = torch.cuda.Stream(dev)
             self._graphs = {}
         e.pp.set_image_shapes(image_shapes if image_shapes is not None else self.input_shape)
-        for slot in (0, 1):
-            if slot not in self._graphs:
-                e.input_slot(slot)
-                self._graphs[slot] = e.capture(self.score, self.nms, slot)
         cs = self._copy_stream
         uploaded = [torch.cuda.Event(), torch.cuda.Event()]   # input slot filled
         consumed = [torch.cuda.Event(), torch.cuda.Event()]   # input slot free again (its graph finished)
         landed = [torch.cuda.Event(), torch.cuda.Event()]     # wire copy of that step on the host
+        kinds = [None, None]  # dtype flavour (uint8 / float32) of the batch sitting in each slot
 
         def upload(images, slot, first_use):
-            if tuple(images.shape) != tuple(e.input.shape) or images.dtype != e.input.dtype:
-                raise ValueError("expected %s %s, got %s %s" % (tuple(e.input.shape), e.input.dtype,
-                                                                tuple(images.shape), images.dtype))
+            dst, u8 = e.slot_for(images, slot)
+            if (slot, u8) not in self._graphs:  # first batch of this flavour in this slot: capture its graph
+                cs.synchronize()
+                main.synchronize()
+                self._graphs[(slot, u8)] = e.capture(self.score, self.nms, slot, u8)
+                main.synchronize()
+            kinds[slot] = u8
             with torch.cuda.stream(cs):
                 if not first_use:
                     cs.wait_event(consumed[slot])
-                e.input_slot(slot).copy_(images, non_blocking=True)
+                dst.copy_(images, non_blocking=True)
                 uploaded[slot].record(cs)
+
+        def finish(p):
+            ps, ph, tk = p
+            landed[ps].synchronize()
+            w = ph.numpy()
+            local = e.pp.unpack_wire(w) if unpack else e.pp.padded_views(w)
+            if gather is None:
+                return local
+            parts = gather.wait(tk) if gather_read else None
+            return local, parts
 
         it = iter(batches)
         try:
@@ -221,14 +235,15 @@ class YOLO(object):
         cs.wait_stream(main)
         upload(cur, 0, True)
         i = 0
-        pending = None  # (slot, host wire tensor) of the previous step, not yet yielded
+        pending = None  # (slot, host wire tensor, gather ticket) of the previous step, not yet yielded
         while cur is not None:
             slot = i & 1
             main.wait_event(uploaded[slot])
-            self._graphs[slot].replay()
+            self._graphs[(slot, kinds[slot])].replay()
             consumed[slot].record(main)
             host = e.pp.enqueue_read(slot)
             landed[slot].record(main)
+            ticket = gather.gather_async(read=gather_read) if gather is not None else None
             try:
                 nxt = next(it)
             except StopIteration:
@@ -236,14 +251,10 @@ class YOLO(object):
             if nxt is not None:
                 upload(nxt, (i + 1) & 1, i == 0)
             if pending is not None:
-                ps, ph = pending
-                landed[ps].synchronize()
-                w = ph.numpy()
-                yield e.pp.unpack_wire(w) if unpack else e.pp.padded_views(w)
-            pending = (slot, host)
+                yield finish(pending)
+            pending = (slot, host, ticket)
             cur = nxt
             i += 1
-        ps, ph = pending
-        landed[ps].synchronize()
-        w = ph.numpy()
-        yield e.pp.unpack_wire(w) if unpack else e.pp.padded_views(w)
+        yield finish(pending)
+        if gather is not None:
+            gather.join()

@@ -52,24 +52,25 @@ class YoloBody:
         if anchors is not None:
             self.anchors = np.asarray(anchors, np.float32).reshape(-1, 2)
         self.engine = Engine(self.model_name, self.num_classes, self.input_hw, self.batch, weights, self.anchors,
-                             **self._kw)
+                             num_anchors=self.num_anchors, **self._kw)
         return self
 
     def load_weights(self, path: str, by_name: bool = False, anchors=None):
         """reference: model.load_weights(path) (code/yolo.py:87, code/yolo3/utils.py:390)."""
         return self.set_weights(load_checkpoint(path, self.netdef.weight_shapes), anchors)
 
-    def __call__(self, x: torch.Tensor) -> List[torch.Tensor]:
+    def __call__(self, x: torch.Tensor, copy: bool = True) -> List[torch.Tensor]:
+        """``[y1, y2, y3]`` raw head logits, each [B, H/s, W/s, 3, C+5].  Like the reference, the returned tensors are
+        fresh (the caller may keep them across calls); ``copy=False`` returns strided views of the engine's persistent
+        output buffers instead, which the next forward / ``detect_*`` call / graph replay overwrites."""
         if self.engine is None:
             raise RuntimeError("weights not loaded: call load_weights()/set_weights() first")
         e = self.engine
-        if tuple(x.shape) != tuple(e.input.shape):
-            raise ValueError("input shape %s != model input %s" % (tuple(x.shape), tuple(e.input.shape)))
-        if x.dtype != e.input.dtype:
-            raise ValueError("input dtype %s != model input dtype %s" % (x.dtype, e.input.dtype))
-        e.input.copy_(x, non_blocking=True)
-        e.run_network()
-        return e.raw_outputs()
+        dst, u8 = e.slot_for(x)
+        dst.copy_(x, non_blocking=True)
+        e.run_network(0, u8)
+        outs = e.raw_outputs()
+        return [y.clone() for y in outs] if copy else outs
 
 
 def yolov3_body(inputs, model_name, num_anchors, **kwargs):
@@ -92,6 +93,9 @@ def yolov3_body(inputs, model_name, num_anchors, **kwargs):
         raise ValueError("only data_format='channels_last' is supported (reference code/yolo.py:208)")
     if model_name not in _BACKBONES:
         raise ValueError("unknown model_name %r" % (model_name,))
+    if int(num_anchors) != 3:
+        # reference: num_anchors // num_scales per scale (code/yolo.py:214-216); every shipped anchor file gives 3
+        raise ValueError("yolov3_body: this engine supports 3 anchors per scale, got %r" % (num_anchors,))
     return YoloBody(shape, model_name, num_anchors, kwargs.get("num_classes", 1000), **eng)
 
 
@@ -229,7 +233,20 @@ class YoloLoss:
         lib = _lib.lib()
         if not (yolo_output.is_cuda and y_true.is_cuda):
             raise _lib.YrError("YoloLoss needs CUDA tensors (no CPU fallback exists)")
+        if yolo_output.dim() != 5 or tuple(y_true.shape) != tuple(yolo_output.shape):
+            raise ValueError("YoloLoss: y_true %s and yolo_output %s must both be [B,gh,gw,A,5+C] with equal shapes"
+                             % (tuple(y_true.shape), tuple(yolo_output.shape)))
+        if y_true.device != yolo_output.device:
+            raise ValueError("YoloLoss: y_true is on %s, yolo_output on %s" % (y_true.device, yolo_output.device))
         B, gh, gw, A, E = (int(v) for v in yolo_output.shape)
+        if A > 3 or A != len(self.anchor) or E < 6:
+            raise ValueError("YoloLoss: expected %d anchors per cell (<= 3) and 5+C >= 6 channels, got A=%d, 5+C=%d"
+                             % (len(self.anchor), A, E))
+        with torch.cuda.device(yolo_output.device):
+            return self._launch(y_true, yolo_output, need_grad, B, gh, gw, A, E)
+
+    def _launch(self, y_true, yolo_output, need_grad, B, gh, gw, A, E):
+        lib = _lib.lib()
         logits, ldl = yolo_output.detach().contiguous(), A * E
         ytrue, ldt = _as_cells_generic(y_true.detach().to(torch.float32), A, E)
         p = YrLossParams()
