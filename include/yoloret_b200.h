@@ -48,7 +48,9 @@ typedef enum yr_op_kind {
     YR_OP_RFCR = 4,      /* fused RFCR fusion: 4x 1x1 conv + resize + weighted sum */
     YR_OP_SE = 5,        /* squeeze-excite gate: global mean -> FC -> swish -> FC -> sigmoid */
     YR_OP_SE_FC = 6,     /* the same gate from the channel sums a DW op left in `aux` (fused squeeze) */
-    YR_OP_MBCONV = 7     /* fused inverted-residual block: 1x1 expand + 3x3 depthwise + 1x1 project (+ residual) */
+    YR_OP_MBCONV = 7,    /* fused inverted-residual block: 1x1 expand + 3x3 depthwise + 1x1 project (+ residual) */
+    YR_OP_DWPW = 8       /* fused 3x3 depthwise (+BN +act) -> 1x1 conv (+BN +act +residual): the depthwise output never
+                            exists in HBM */
 } yr_op_kind;
 
 typedef enum yr_resample_mode { YR_UP2 = 0, YR_POOL2 = 1, YR_POOL4 = 2 } yr_resample_mode;
@@ -93,6 +95,12 @@ typedef enum yr_resample_mode { YR_UP2 = 0, YR_POOL2 = 1, YR_POOL4 = 2 } yr_resa
  *           depthwise, linear project; res optional [B,Ho,Wo,ld_res] (stride 1); w_tc = yr_mbconv_pack image
  *           of the three layers' folded weights; out [B,Ho,Wo,ld_out].  One kernel for block_N_expand ..
  *           block_N_add of tf.keras.applications.MobileNetV2 (reference code/yolo3/override.py:339-341).
+ *  DWPW     in [B,H,W,ld_in] C channels (multiple of 8); k=3, stride 1|2, pad_t/pad_l = leading TF-SAME pads;
+ *           mode = yr_act of the depthwise conv; N = output channels of the 1x1 conv (<= 192), act = its activation;
+ *           bias = the 1x1 conv's bias [N]; res optional [B,Ho,Wo,ld_res]; w_tc = yr_dwpw_pack image (both layers'
+ *           folded weights); out [B,Ho,Wo,ld_out].  Bit-identical to a DW op followed by a PW op (variant 2/3).
+ *           One kernel for block_N_depthwise .. block_N_project(+add) of tf.keras.applications.MobileNetV2
+ *           (reference code/yolo3/override.py:339-341) and the SE-less MBConv blocks of efficientnet.py:501-533.
  *  SE       in [B,H,W,ld_in] C=F channels; w = [F][R] then [R][F] (w2 = w + F*R),
  *           bias = b1[R] then b2[F]; N = R; out = gate [B][F].
  *           SEBlock, efficientnet.py:406-438.
@@ -100,7 +108,7 @@ typedef enum yr_resample_mode { YR_UP2 = 0, YR_POOL2 = 1, YR_POOL4 = 2 } yr_resa
 typedef struct yr_op {
     int32_t kind;      /* yr_op_kind */
     int32_t act;       /* yr_act */
-    int32_t mode;      /* yr_resample_mode (RESAMPLE) */
+    int32_t mode;      /* yr_resample_mode (RESAMPLE); yr_act of the depthwise conv (DWPW) */
     int32_t in_is_u8;  /* STEM */
     int32_t B, H, W, C;      /* input batch / height / width / channels (K) */
     int32_t Ho, Wo, N;       /* output height / width / channels */
@@ -153,6 +161,14 @@ int yr_pw_ts_pack(const float* w, int K, int N, float* packed, void* stream);
 int64_t yr_mbconv_packed_floats(int Cin, int Ce, int Cout);
 int yr_mbconv_pack(const float* w1, int ld1, const float* b1, const float* wd, int ldd, const float* b2,
                    const float* w2, int ld2, const float* b3, int Cin, int Ce, int Cout, float* packed, void* stream);
+
+/* Fused depthwise -> pointwise pair (YR_OP_DWPW): w_pw [K][N] (the PW op's `w`), w_dw [9][K] + b_dw [K] (the DW op's
+ * `w` / `bias`; K = the depthwise channel count = the 1x1 conv's input channels).  yr_dwpw_packed_floats returns 0
+ * when N needs more than one n tile (> 192); yr_dwpw_supported says whether a given layer geometry has a fused
+ * tiling (the caller otherwise runs the two ops separately). */
+int64_t yr_dwpw_packed_floats(int K, int N);
+int yr_dwpw_pack(const float* w_pw, int K, int N, const float* w_dw, const float* b_dw, float* packed, void* stream);
+int yr_dwpw_supported(int C, int N, int stride, int Ho, int Wo);
 
 /* ---- post-process: yolo_eval (reference code/yolo3/model.py:431-491) --------- */
 

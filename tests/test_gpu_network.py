@@ -78,6 +78,26 @@ def test_fused_blocks_equal_unfused(built_lib, anchors):
         assert torch.equal(a, b), float((a - b).abs().max())
 
 
+@pytest.mark.parametrize("name,hw,B", [("mobilenetv2x75", (128, 160), 3), ("mobilenetv2x14", (96, 96), 2),
+                                       ("efficientnetlite0", (96, 128), 2), ("efficientnetb3", (64, 96), 2)])
+def test_fused_depthwise_pointwise_equals_separate(built_lib, anchors, name, hw, B):
+    """Engine with the fused depthwise->pointwise kernel (YR_OP_DWPW, default on) == engine running the two layers
+    separately, bit for bit, with fewer launches; SE blocks (EfficientNet-B3) keep their separate kernels."""
+    ncls = 80
+    nd = NetDef(name, ncls, hw)
+    w = synthetic_weights(nd.weight_shapes, ncls, seed=41)
+    x = torch.rand(B, hw[0], hw[1], 3, generator=torch.Generator().manual_seed(7)).cuda()
+    mf = yolov3_body((B, hw[0], hw[1], 3), name, 3, num_classes=ncls, fuse_dwpw=True).set_weights(w, anchors)
+    mu = yolov3_body((B, hw[0], hw[1], 3), name, 3, num_classes=ncls, fuse_dwpw=False).set_weights(w, anchors)
+    assert len(mu.engine.dwpw_blob) == 0
+    if name != "efficientnetb3":
+        assert len(mf.engine.dwpw_blob) >= 5
+    yf, yu = mf(x), mu(x)
+    for a, b in zip(yf, yu):
+        assert torch.equal(a, b), float((a - b).abs().max())
+    assert mf.engine.build_plan(0, B)[1] == mu.engine.build_plan(0, B)[1] - len(mf.engine.dwpw_blob)
+
+
 def test_fused_upsampling_equals_separate_resample(built_lib, anchors):
     """The engine folds UpSampling2D into the producing 1x1 conv's epilogue (block_20_conv / block_24_conv): logits
     bit-identical to running the resample op on its own, with fewer launches."""

@@ -170,6 +170,84 @@ def test_dw_parity(built_lib, B, H, W, C, k, s, act, pad_ld):
         assert torch.isnan(out[..., :off]).all() and torch.isnan(out[..., off + C:]).all()
 
 
+@pytest.mark.parametrize("B,H,W,C,N,s,dw_act,pw_act,use_res", [
+    (2, 16, 16, 96, 24, 1, "relu6", "none", True),      # one tile per image, resident weights
+    (3, 104, 104, 144, 24, 1, "relu6", "none", True),   # block_2: many tiles, C not a multiple of 32
+    (2, 104, 104, 144, 24, 2, "relu6", "none", False),  # block_3: stride 2, TF SAME pads (0,1)
+    (2, 208, 208, 96, 24, 2, "relu6", "none", False),   # block_1
+    (2, 208, 208, 24, 16, 1, "relu6", "none", False),   # expanded_conv: narrow K
+    (3, 52, 52, 144, 48, 1, "relu6", "none", True),
+    (2, 26, 26, 288, 72, 1, "relu6", "none", True),
+    (3, 26, 26, 432, 72, 1, "relu6", "none", False),    # streamed weight ring
+    (2, 26, 26, 432, 120, 2, "relu6", "none", False),   # block_13: odd output 13x13, pads (0,1), streamed
+    (5, 13, 13, 720, 120, 1, "relu6", "none", True),    # 13x13: two ragged tiles per image
+    (2, 61, 45, 64, 40, 2, "none", "relu6", False),     # odd sizes, other activations
+    (2, 17, 23, 40, 192, 1, "swish", "swish", True),    # widest single n tile
+    (1, 5, 3, 8, 8, 1, "relu6", "none", False),
+])
+def test_dwpw_bit_identical_to_separate_ops(built_lib, B, H, W, C, N, s, dw_act, pw_act, use_res):
+    """YR_OP_DWPW (3x3 depthwise + BN + act computed by the converter warps of the tcgen05 pointwise kernel) gives the
+    same BITS as the depthwise op followed by the pointwise op (variant 3), and matches an fp64 reference; concat-slice
+    leading dimensions on both sides; repeated launches are bit-stable (ring protocol)."""
+    x = _rand(B, H, W, C, seed=31)
+    wd = _rand(9, C, seed=32, scale=0.3).cuda()
+    bd = _rand(C, seed=33).cuda()
+    wp = _rand(C, N, seed=34, scale=C ** -0.5).cuda()
+    bp = _rand(N, seed=35).cuda()
+    ref_dw, (Ho, Wo, pt, pl) = _dw_ref(x, wd.cpu(), bd.cpu(), 3, s, dw_act)
+    res = _rand(B, Ho, Wo, N, seed=36).cuda() if use_res else None
+    ref = act_ref(ref_dw @ wp.double().cpu() + bp.double().cpu(), pw_act)
+    if use_res:
+        ref = ref + res.double().cpu()
+    ld_in, off = C + 16, 8
+    xw = torch.full((B, H, W, ld_in), float("nan"), device="cuda")
+    xw[..., off:off + C] = x.cuda()
+    # separate ops
+    mid = torch.full((B, Ho, Wo, C), float("nan"), device="cuda")
+    op = YrOp()
+    op.kind, op.act = _lib.OP_DW, ACT[dw_act]
+    op.B, op.H, op.W, op.C, op.Ho, op.Wo, op.N = B, H, W, C, Ho, Wo, C
+    op.k, op.stride, op.pad_t, op.pad_l, op.ld_in, op.ld_out = 3, s, pt, pl, ld_in, C
+    op.in_, op.out, op.w, op.bias = xw.data_ptr() + 4 * off, mid.data_ptr(), wd.data_ptr(), bd.data_ptr()
+    run_op(op)
+    sep = pw_op(mid, wp, bp, pw_act, res=res, variant=3, ld_out=N + 8)
+    # fused
+    lib = _lib.lib()
+    assert lib.yr_dwpw_supported(C, N, s, Ho, Wo) == 1
+    n = int(lib.yr_dwpw_packed_floats(C, N))
+    blob = torch.full((n,), float("nan"), device="cuda")
+    _lib.check(lib.yr_dwpw_pack(wp.data_ptr(), C, N, wd.data_ptr(), bd.data_ptr(), blob.data_ptr(),
+                                torch.cuda.current_stream().cuda_stream), "yr_dwpw_pack")
+    torch.cuda.synchronize()
+    assert not torch.isnan(blob).any()
+    out = torch.full((B, Ho, Wo, N + 8), float("nan"), device="cuda")
+    f = YrOp()
+    f.kind, f.act, f.mode = _lib.OP_DWPW, ACT[pw_act], ACT[dw_act]
+    f.B, f.H, f.W, f.C, f.Ho, f.Wo, f.N = B, H, W, C, Ho, Wo, N
+    f.k, f.stride, f.pad_t, f.pad_l, f.ld_in, f.ld_out = 3, s, pt, pl, ld_in, N + 8
+    f.in_, f.out, f.w_tc, f.bias = xw.data_ptr() + 4 * off, out.data_ptr(), blob.data_ptr(), bp.data_ptr()
+    if use_res:
+        f.res, f.ld_res = res.data_ptr(), N
+    run_op(f)
+    assert torch.equal(out[..., :N], sep[..., :N]), float((out[..., :N] - sep[..., :N]).abs().max())
+    assert torch.isnan(out[..., N:]).all()
+    torch.testing.assert_close(out[..., :N].cpu().double(), ref, rtol=1e-4, atol=1e-4)
+    first = out.clone()
+    for _ in range(5):
+        run_op(f)
+        assert torch.equal(first[..., :N], out[..., :N])
+
+
+def test_dwpw_rejects_unfusable(built_lib):
+    lib = _lib.lib()
+    assert lib.yr_dwpw_supported(1344, 224, 1, 19, 19) == 0      # two n tiles: the depthwise would be recomputed
+    assert int(lib.yr_dwpw_packed_floats(1344, 224)) == 0
+    f = YrOp()
+    f.kind = _lib.OP_DWPW
+    with pytest.raises(_lib.YrError):
+        run_op(f)
+
+
 @pytest.mark.parametrize("u8", [False, True])
 @pytest.mark.parametrize("H,W,N,act", [(32, 32, 24, "relu6"), (33, 47, 40, "swish"),  # odd size: the generic kernel
                                        (96, 160, 24, "relu6"), (70, 52, 48, "relu6"), (37, 44, 32, "swish"),

@@ -30,6 +30,18 @@
 // TMEM map (512 columns): [nAcc accumulators x acc_stride][nT A stages x (32 hi + 32 lo) columns].
 // Output channels are cut into n tiles of <= 192 columns; work items run m-major so the n tiles of one
 // 128-row block are consecutive and re-read their A tile from L2.
+//
+// DEPTHWISE FRONT (YR_OP_DWPW, template FRONT = stride 1 | 2): the same kernel with the 3x3 depthwise conv + BN +
+// activation that PRECEDES the 1x1 conv computed by the converter warps, so the depthwise output - the widest tensor
+// of an inverted-residual block (reference tf.keras.applications.MobileNetV2 blocks behind code/yolo3/override.py:339,
+// MBConvBlock code/yolo3/efficientnet.py:501-522) - never exists in HBM: one write and one read of the 6x-expanded
+// tensor less per block.  A work item is a TH x TW tile of output pixels of one image (<= 128 pixels = the 128 rows of
+// the MMA); per 32-channel k-block the A producer brings the halo'd input box with ONE 4-D TMA (
+// out-of-image coordinates zero-filled = TF 'SAME' padding); a converter group first computes the depthwise conv
+// register-tiled like dw_tma_kernel (thread = 4 channels x 2 x 4 pixels, same operation order: bit-identical to running
+// the two layers separately; taps and bias of the k-block ride at the end of the weight slot) into a 16 KB staging tile,
+// then each thread takes one tile row (= its TMEM lane), splits it into (hi, lo) and writes tensor memory.
+// The MMA issuer, weight producer and epilogue are unchanged apart from the row -> pixel mapping of the stores.
 #include "tc_common.cuh"
 
 namespace yr {
@@ -60,8 +72,15 @@ struct Params {
     int up2, img_w;  // up2: every output row is stored to its 2x2 nearest-upsampled pixels (fused UpSampling2D)
     int nA, nT, nB, nAcc, resident, acc_stride, a_col0, items_per_cta, total_items, epi_group_bytes;
     uint32_t idesc;
+    uint32_t a_slot_bytes, b_slot_bytes;  // ring slot sizes (depthwise front: halo'd box / weight slot + dw taps)
+    // depthwise front: spatial tiling of the output (an item = one TH x TW tile of one image)
+    int TH, TW, IW, tiles_h, tiles_w, Ho, Wo, pad_t, pad_l, dw_act;
+    int w_rep;             // copies of the weight image in global memory (CTA i streams copy i % w_rep)
+    size_t w_rep_stride;   // bytes between copies
+    int epi_groups;  // 2 (the groups alternate tiles) or 1 (stride-2 depthwise front: shared memory goes to the boxes)
     long long* dbg;
 };
+constexpr int DW_TAIL_BYTES = 2048;  // per weight slot: 9 x 32 depthwise taps + 32 biases (1280 B), padded to 2 KB
 
 constexpr int BAR_A_FULL = 0;
 constexpr int BAR_A_EMPTY = BAR_A_FULL + MAX_A;
@@ -105,10 +124,16 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- epilogue (see pwconv_tc.cu for the access pattern; items here are m-major) ---------------
-template <int ACT, bool HAS_RES, bool UP2, bool DBG>
+template <int ACT, bool HAS_RES, bool UP2, bool DBG, bool SP = false>
 __device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, const float* s_bias, uint32_t tmem_base,
                                               uint32_t bar0, int item0, int item1, int q, int lane, int ewarp, int grp) {
     const int sub_r = lane >> 3;
@@ -117,11 +142,24 @@ __device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, const
     Ring racc;
     int mt = item0 / p.n_tiles, nt = item0 - mt * p.n_tiles;
     for (int item = item0; item < item1; ++item, ++it) {
-        if ((int)(it & 1u) == grp) {
+        if (p.epi_groups == 1 ? grp == 0 : (int)(it & 1u) == grp) {
             const uint32_t acc = racc.slot;
             const int row0 = mt * BM + q * 32;
             const int ncols = min(p.BN, p.N - nt * p.BN);
-            const int rows = min(32, p.M - row0);
+            const int rows = SP ? 32 : min(32, p.M - row0);
+            // depthwise front: tile row -> output pixel of the [B, Ho, Wo] tensor (-1 = outside the tile / image)
+            int pix[8];
+            if (SP) {
+                const int tw = mt % p.tiles_w, r2 = mt / p.tiles_w;
+                const int th = r2 % p.tiles_h, bi = r2 / p.tiles_h;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = q * 32 + sub_r + 4 * i;
+                    const int ty = r / p.TW, tx = r - ty * p.TW;
+                    const int y = th * p.TH + ty, x = tw * p.TW + tx;
+                    pix[i] = (ty < p.TH && y < p.Ho && x < p.Wo) ? (bi * p.Ho + y) * p.Wo + x : -1;
+                }
+            }
             const uint32_t tsrc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.acc_stride;
             bool waited = false;
             float v[32];
@@ -133,9 +171,14 @@ __device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, const
                 if (HAS_RES) {
                     const float* rp = p.res + (size_t)(row0 + sub_r) * p.ld_res + n;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        rv[i] = (col_ok && sub_r + 4 * i < rows) ? ldg4(rp + (size_t)(4 * i) * p.ld_res)
-                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int i = 0; i < 8; ++i) {
+                        if (SP)
+                            rv[i] = (col_ok && pix[i] >= 0) ? ldg4(p.res + (size_t)pix[i] * p.ld_res + n)
+                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+                        else
+                            rv[i] = (col_ok && sub_r + 4 * i < rows) ? ldg4(rp + (size_t)(4 * i) * p.ld_res)
+                                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                 }
                 if (!waited) {
                     mbar_wait(bar0 + 8u * (BAR_ACC_FULL + acc), racc.phase, 6);
@@ -160,14 +203,16 @@ __device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, const
                     const size_t ostep = (size_t)4 * p.ld_out;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        if (sub_r + 4 * i < rows) {
+                        if (SP ? (pix[i] >= 0) : (sub_r + 4 * i < rows)) {
                             float4 x = *reinterpret_cast<const float4*>(sp + (4 * i) * EPI_LD);
                             x.x = apply_act<ACT>(x.x + bv.x);
                             x.y = apply_act<ACT>(x.y + bv.y);
                             x.z = apply_act<ACT>(x.z + bv.z);
                             x.w = apply_act<ACT>(x.w + bv.w);
                             if (HAS_RES) { x.x += rv[i].x; x.y += rv[i].y; x.z += rv[i].z; x.w += rv[i].w; }
-                            if (!UP2) {
+                            if (SP) {
+                                st4(p.out + (size_t)pix[i] * p.ld_out + n, x);
+                            } else if (!UP2) {
                                 st4(op + (size_t)i * ostep, x);
                             } else {
                                 // fused UpSampling2D (nearest x2, reference code/yolo3/model.py:254,274): input pixel
@@ -272,18 +317,155 @@ __device__ __forceinline__ void converter_loop(const Params& p, const uint8_t* a
     }
 }
 
-template <bool DBG>
+// ---- depthwise front: the converter group computes the 3x3 depthwise conv of the tile from the halo'd box ------
+// Two phases per 32-channel k-block, both by the 128 threads of one converter group:
+//   1. register-tiled depthwise conv exactly as dw_tma_kernel does it (thread = 4 channels x a 2 x 4 pixel patch:
+//      24 (stride 2: 45) LDS.128 of the box for 32 outputs, 8 lanes cover a 128-byte pixel = conflict-free; same
+//      operation order: acc = 0; acc = fma(x, w, acc) over (kh, kw) row-major; act(acc + bias)), results written to a
+//      16 KB staging tile [128 pixels][32 channels] whose 16-byte chunks are XOR-swizzled with (row & 7);
+//   2. the plain converter: thread = tile row = TMEM lane reads its 128-byte row (8 conflict-free LDS.128), splits
+//      into (hi, lo) TF32 and writes tensor memory.
+// The taps and bias of the k-block ride in the tail of the weight slot.  Named barrier 3 + group fences the staging tile.
+template <int S, bool DBG>
+__device__ __forceinline__ void dw_converter_loop(const Params& p, const uint8_t* a_ring, const uint8_t* b_ring,
+                                                  float* stage, uint32_t tmem_base, uint32_t bar0, int item0, int item1,
+                                                  int q, int lane, int grp) {
+    constexpr int PH = 2, PW = 4, KS = 3;
+    constexpr int IN_ROWS = (PH - 1) * S + KS, IN_COLS = (PW - 1) * S + KS;
+    Ring ra, rt, rb;
+    uint32_t dq = 0, b_seen = 0;
+    const int gtid = q * 32 + lane;           // thread of the group; also the tile row / TMEM lane of phase 2
+    const int cq = gtid & 7;                  // phase 1: channel quad (16-byte chunk of the pixel)
+    const int pg = gtid >> 3;                 // phase 1: pixel patch
+    const int gw = p.TW / PW;
+    const int gx = pg % gw, gy = pg / gw;
+    const int box_off = ((gy * PH * S) * p.IW + gx * PW * S) * BK + cq * 4;  // floats
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)p.a_col0;
+    const uint32_t dw_off = 2u * p.BN * 128u;
+    const uint32_t bar_id = 3u + (uint32_t)grp;
+    for (int item = item0; item < item1; ++item) {
+        for (int kb = 0; kb < p.KB; ++kb, ++dq) {
+            if ((int)(dq & 1u) == grp) {
+                uint32_t bslot;
+                if (p.resident) {
+                    bslot = (uint32_t)kb;
+                    if (!((b_seen >> bslot) & 1u)) {
+                        mbar_wait(bar0 + 8u * (BAR_B_FULL + bslot), 0, 8);
+                        b_seen |= 1u << bslot;
+                    }
+                } else {
+                    bslot = rb.slot;
+                    mbar_wait(bar0 + 8u * (BAR_B_FULL + bslot), rb.phase, 8);
+                }
+                mbar_wait(bar0 + 8u * (BAR_A_FULL + ra.slot), ra.phase, 5);
+                if (q == 0 && lane == 0) dbg_mark(p, 1, dq);
+                // ---- phase 1: depthwise conv of this thread's patch ----
+                const float* sx = reinterpret_cast<const float*>(a_ring + (size_t)ra.slot * p.a_slot_bytes) + box_off;
+                const float4* wd = reinterpret_cast<const float4*>(b_ring + (size_t)bslot * p.b_slot_bytes + dw_off) + cq;
+                float4 acc[PH][PW];
+#pragma unroll
+                for (int t = 0; t < PH; ++t)
+#pragma unroll
+                    for (int o = 0; o < PW; ++o) acc[t][o] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int rr = 0; rr < IN_ROWS; ++rr) {
+                    float4 x[IN_COLS];
+                    const float* row = sx + (size_t)rr * p.IW * BK;
+#pragma unroll
+                    for (int j = 0; j < IN_COLS; ++j) x[j] = *reinterpret_cast<const float4*>(row + j * BK);
+#pragma unroll
+                    for (int t = 0; t < PH; ++t) {
+                        const int kh = rr - t * S;
+                        if (kh < 0 || kh >= KS) continue;
+#pragma unroll
+                        for (int kw = 0; kw < KS; ++kw) {
+                            const float4 ww = wd[(kh * KS + kw) * 8];
+#pragma unroll
+                            for (int o = 0; o < PW; ++o) {
+                                const float4 xv = x[o * S + kw];
+                                acc[t][o].x = fmaf(xv.x, ww.x, acc[t][o].x);
+                                acc[t][o].y = fmaf(xv.y, ww.y, acc[t][o].y);
+                                acc[t][o].z = fmaf(xv.z, ww.z, acc[t][o].z);
+                                acc[t][o].w = fmaf(xv.w, ww.w, acc[t][o].w);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar0 + 8u * (BAR_A_EMPTY + ra.slot));  // this warp is done with the box
+                const float4 bv = wd[72];
+                // the staging tile may still be read by phase 2 of this group's previous k-block
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+#pragma unroll
+                for (int t = 0; t < PH; ++t) {
+#pragma unroll
+                    for (int o = 0; o < PW; ++o) {
+                        float4 v;
+                        v.x = apply_act_rt(acc[t][o].x + bv.x, p.dw_act);
+                        v.y = apply_act_rt(acc[t][o].y + bv.y, p.dw_act);
+                        v.z = apply_act_rt(acc[t][o].z + bv.z, p.dw_act);
+                        v.w = apply_act_rt(acc[t][o].w + bv.w, p.dw_act);
+                        const int r = (gy * PH + t) * p.TW + gx * PW + o;
+                        *reinterpret_cast<float4*>(stage + r * BK + ((cq ^ (r & 7)) << 2)) = v;
+                    }
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                // ---- phase 2: row gtid of the staging tile -> (hi, lo) TF32 columns of the TMEM stage ----
+                float4 v[8];
+                {
+                    const float* rowp = stage + gtid * BK;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(rowp + ((c ^ (gtid & 7)) << 2));
+                }
+                mbar_wait(bar0 + 8u * (BAR_T_EMPTY + rt.slot), rt.phase ^ 1u, 7);
+                tc_fence_after();
+                if (q == 0 && lane == 0) dbg_mark(p, 2, dq);
+                const uint32_t taddr = lane_base + rt.slot * (uint32_t)T_STAGE_COLS;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t h[16], l[16];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 x = v[half * 4 + j];
+                        const float hx = tf32_rna(x.x), hy = tf32_rna(x.y), hz = tf32_rna(x.z), hw = tf32_rna(x.w);
+                        h[4 * j + 0] = __float_as_uint(hx);
+                        h[4 * j + 1] = __float_as_uint(hy);
+                        h[4 * j + 2] = __float_as_uint(hz);
+                        h[4 * j + 3] = __float_as_uint(hw);
+                        l[4 * j + 0] = __float_as_uint(tf32_rna(x.x - hx));
+                        l[4 * j + 1] = __float_as_uint(tf32_rna(x.y - hy));
+                        l[4 * j + 2] = __float_as_uint(tf32_rna(x.z - hz));
+                        l[4 * j + 3] = __float_as_uint(tf32_rna(x.w - hw));
+                    }
+                    tmem_st16(taddr + half * 16, h);
+                    tmem_st16(taddr + 32 + half * 16, l);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar0 + 8u * (BAR_T_FULL + rt.slot));
+                if (q == 0 && lane == 0) dbg_mark(p, 3, dq);
+            }
+            ra.advance(p.nA);
+            rt.advance(p.nT);
+            if (!p.resident) rb.advance(p.nB);
+        }
+    }
+}
+
+template <bool DBG, int FRONT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [raw A ring: nA x 16K][weight slots: nB x (hi | lo)][epilogue: 2 x (transpose + bias)][barriers]
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t b_slot_bytes = 2u * p.BN * 128u;
+    const uint32_t b_slot_bytes = p.b_slot_bytes;
     const uint32_t a_off = 0;
-    const uint32_t b_off = a_off + p.nA * (uint32_t)A_TILE_BYTES;
+    const uint32_t b_off = a_off + p.nA * p.a_slot_bytes;
     const uint32_t epi_off = b_off + p.nB * b_slot_bytes;
-    const uint32_t bar_off = epi_off + 2u * (uint32_t)p.epi_group_bytes;
+    const uint32_t stage_off = epi_off + (uint32_t)(p.epi_groups * p.epi_group_bytes);  // depthwise front: 2 staging tiles
+    const uint32_t bar_off = stage_off + (FRONT != 0 ? 2u * (uint32_t)A_TILE_BYTES : 0u);
     const uint32_t bar0 = base + bar_off;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gbase + bar_off + 8u * BAR_COUNT);
 
@@ -337,11 +519,24 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
             uint32_t dq = 0;
             int mt = item0 / p.n_tiles, nt = item0 - mt * p.n_tiles;
             for (int item = item0; item < item1; ++item) {
+                int bx = 0, by = 0, bimg = 0;  // depthwise front: box origin of this item's tile (input coordinates)
+                uint32_t box_bytes = A_TILE_BYTES;
+                if constexpr (FRONT != 0) {
+                    const int tw = mt % p.tiles_w, r2 = mt / p.tiles_w;
+                    bx = tw * p.TW * FRONT - p.pad_l;
+                    by = (r2 % p.tiles_h) * p.TH * FRONT - p.pad_t;
+                    bimg = r2 / p.tiles_h;
+                    box_bytes = (uint32_t)(((p.TH - 1) * FRONT + 3) * p.IW) * 128u;
+                }
                 for (int kb = 0; kb < p.KB; ++kb) {
                     mbar_wait(bar0 + 8u * (BAR_A_EMPTY + ra.slot), ra.phase ^ 1u, 1);
-                    mbar_expect_tx(bar0 + 8u * (BAR_A_FULL + ra.slot), A_TILE_BYTES);
-                    tma_load_2d(base + a_off + ra.slot * (uint32_t)A_TILE_BYTES, &tmA, bar0 + 8u * (BAR_A_FULL + ra.slot),
-                                kb * BK, mt * BM);
+                    mbar_expect_tx(bar0 + 8u * (BAR_A_FULL + ra.slot), box_bytes);
+                    if constexpr (FRONT != 0)
+                        tma_load_4d(base + a_off + ra.slot * p.a_slot_bytes, &tmA, bar0 + 8u * (BAR_A_FULL + ra.slot), kb * BK,
+                                    bx, by, bimg);
+                    else
+                        tma_load_2d(base + a_off + ra.slot * p.a_slot_bytes, &tmA, bar0 + 8u * (BAR_A_FULL + ra.slot),
+                                    kb * BK, mt * BM);
                     dbg_mark(p, 0, dq++);
                     ra.advance(p.nA);
                 }
@@ -353,7 +548,7 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
         if (lane == 0) {
             Ring rb;
             int nt = item0 % p.n_tiles;
-            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wp);
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wp) + (size_t)(blockIdx.x % (unsigned)p.w_rep) * p.w_rep_stride;
             if (p.resident) {  // the whole weight image once, first-needed slots first
                 const int total = p.n_tiles * p.KB;
                 for (int i = 0; i < total; ++i) {
@@ -428,7 +623,11 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
         }
     } else if (warp < 2 + NUM_CONVERTERS / 32) {
         const int cw = warp - 2;
-        if (p.scale != nullptr) converter_loop<true, DBG>(p, gbase + a_off, tmem_base, bar0, item0, item1, warp & 3, lane, cw >> 2);
+        if constexpr (FRONT != 0)
+            dw_converter_loop<FRONT ? FRONT : 1, DBG>(p, gbase + a_off, gbase + b_off,
+                                                       reinterpret_cast<float*>(gbase + stage_off + (cw >> 2) * A_TILE_BYTES), tmem_base,
+                                                       bar0, item0, item1, warp & 3, lane, cw >> 2);
+        else if (p.scale != nullptr) converter_loop<true, DBG>(p, gbase + a_off, tmem_base, bar0, item0, item1, warp & 3, lane, cw >> 2);
         else converter_loop<false, DBG>(p, gbase + a_off, tmem_base, bar0, item0, item1, warp & 3, lane, cw >> 2);
     } else if (warp < 2 + (NUM_CONVERTERS + NUM_EPILOGUE) / 32) {
         // ===== epilogue =====
@@ -436,25 +635,43 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
         const int ew = ew8 & 3, eg = ew8 >> 2;
         float* stg = reinterpret_cast<float*>(gbase + epi_off + eg * p.epi_group_bytes) + ew * 32 * EPI_LD;
         float* s_bias = reinterpret_cast<float*>(gbase + epi_off + eg * p.epi_group_bytes + EPI_STAGE_BYTES);
+        if (eg < p.epi_groups) {  // (a single-group launch leaves the second group's warps idle: it has no buffers)
         // every n tile's bias, once (named barrier 1+eg = the 4 warps of this epilogue group)
         for (int i = ew * 32 + lane; i < p.n_tiles * p.BN; i += 128) s_bias[i] = i < p.N ? __ldg(p.bias + i) : 0.0f;
         asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
         const bool has_res = p.res != nullptr;
-        switch (p.act) {
-            case YR_ACT_RELU6:
-                if (has_res) epilogue_loop<YR_ACT_RELU6, true, false, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                else if (p.up2) epilogue_loop<YR_ACT_RELU6, false, true, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                else epilogue_loop<YR_ACT_RELU6, false, false, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                break;
-            case YR_ACT_SWISH:
-                if (has_res) epilogue_loop<YR_ACT_SWISH, true, false, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                else if (p.up2) epilogue_loop<YR_ACT_SWISH, false, true, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                else epilogue_loop<YR_ACT_SWISH, false, false, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                break;
-            default:
-                if (has_res) epilogue_loop<YR_ACT_NONE, true, false, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                else if (p.up2) epilogue_loop<YR_ACT_NONE, false, true, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
-                else epilogue_loop<YR_ACT_NONE, false, false, DBG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg);
+#define YR_EPI(ACT_, RES_, UP_, SP_) \
+    epilogue_loop<ACT_, RES_, UP_, DBG, SP_>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg)
+        if constexpr (FRONT != 0) {  // depthwise front: rows are pixels of a spatial tile (no fused upsampling here)
+            switch (p.act) {
+                case YR_ACT_RELU6:
+                    if (has_res) YR_EPI(YR_ACT_RELU6, true, false, true); else YR_EPI(YR_ACT_RELU6, false, false, true);
+                    break;
+                case YR_ACT_SWISH:
+                    if (has_res) YR_EPI(YR_ACT_SWISH, true, false, true); else YR_EPI(YR_ACT_SWISH, false, false, true);
+                    break;
+                default:
+                    if (has_res) YR_EPI(YR_ACT_NONE, true, false, true); else YR_EPI(YR_ACT_NONE, false, false, true);
+            }
+        } else {
+            switch (p.act) {
+                case YR_ACT_RELU6:
+                    if (has_res) YR_EPI(YR_ACT_RELU6, true, false, false);
+                    else if (p.up2) YR_EPI(YR_ACT_RELU6, false, true, false);
+                    else YR_EPI(YR_ACT_RELU6, false, false, false);
+                    break;
+                case YR_ACT_SWISH:
+                    if (has_res) YR_EPI(YR_ACT_SWISH, true, false, false);
+                    else if (p.up2) YR_EPI(YR_ACT_SWISH, false, true, false);
+                    else YR_EPI(YR_ACT_SWISH, false, false, false);
+                    break;
+                default:
+                    if (has_res) YR_EPI(YR_ACT_NONE, true, false, false);
+                    else if (p.up2) YR_EPI(YR_ACT_NONE, false, true, false);
+                    else YR_EPI(YR_ACT_NONE, false, false, false);
+            }
+        }
+#undef YR_EPI
         }
     }
 
@@ -468,7 +685,7 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
 // W [K][N] row-major -> per (n tile, k block): [hi tile | lo tile], each BN rows (n) x 32 k-floats in the
 // K-major SWIZZLE_128B image the MMA's B descriptor reads, zero padded (same format as pwconv_tc.cu).
 __global__ void pack_kernel(const float* __restrict__ w, int K, int N, int BN, int n_tiles, int KB,
-                            float* __restrict__ packed) {
+                            float* __restrict__ packed, int tail_floats) {
     const long long total = (long long)n_tiles * KB * BN * BK;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -479,16 +696,53 @@ __global__ void pack_kernel(const float* __restrict__ w, int K, int N, int BN, i
     const int n = nt * BN + r, k = kb * BK + kk;
     const float v = (n < N && k < K) ? w[(size_t)k * N + n] : 0.f;
     const float h = tf32_rna(v), l = tf32_rna(v - h);
-    const size_t slot_floats = (size_t)2 * BN * BK;
+    const size_t slot_floats = (size_t)2 * BN * BK + tail_floats;
     const size_t off = (size_t)(r >> 3) * 256 + (size_t)(r & 7) * 32 + (size_t)(((kk >> 2) ^ (r & 7)) << 2) + (kk & 3);
     float* slot = packed + ((size_t)nt * KB + kb) * slot_floats;
     slot[off] = h;
     slot[(size_t)BN * BK + off] = l;
 }
 
+// depthwise front: per k-block the 9 x 32 taps ([tap][channel]) and the 32 biases behind the (hi | lo) weight tiles
+__global__ void pack_dw_tail_kernel(const float* __restrict__ w_dw, const float* __restrict__ b_dw, int K, int KB,
+                                    size_t slot_floats, size_t tail_off, float* __restrict__ packed) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= KB * (DW_TAIL_BYTES / 4)) return;
+    const int kb = idx / (DW_TAIL_BYTES / 4), e = idx % (DW_TAIL_BYTES / 4);
+    float v = 0.f;
+    const int k = kb * BK + (e & 31);
+    if (k < K) {
+        if (e < 288) v = w_dw[(size_t)(e >> 5) * K + k];
+        else if (e < 320) v = b_dw[k];
+    }
+    packed[(size_t)kb * slot_floats + tail_off + e] = v;
+}
+
+// Copies of a streamed weight image: every SM streams the SAME image from L2 for every row block, so its lines are hot
+// spots of a few L2 slices; copy i % R at a different address spreads the load (experiment knob YR_PW_WREP, default 1).
+inline int weight_replicas() {
+    static const int v = [] {
+        const char* e = getenv("YR_PW_WREP");
+        const int r = e ? atoi(e) : 1;
+        return r >= 1 && r <= 16 ? r : 1;
+    }();
+    return v;
+}
+inline int a_ring_for_streamed() {  // experiment knob YR_PW_STREAM_NA: raw A tiles kept when weights are streamed
+    static const int v = [] {
+        const char* e = getenv("YR_PW_STREAM_NA");
+        const int r = e ? atoi(e) : 4;
+        return r >= 2 && r <= 8 ? (r & ~1) : 4;
+    }();
+    return v;
+}
+
 struct Tiling {
     int BN, n_tiles, KB, nA, nT, nB, nAcc, resident, acc_stride, a_col0, epi_group_bytes;
     size_t smem;
+    // depthwise front
+    int TH, TW, IH, IW, tiles_h, tiles_w, epi_groups;
+    uint32_t a_slot, b_slot;
 };
 
 static bool make_tiling(int K, int N, Tiling& t) {
@@ -516,8 +770,8 @@ static bool make_tiling(int K, int N, Tiling& t) {
         // streamed: the MMA issuer waits on weights (L2 latency ~2k cycles against ~800 cycles of MMA per slot), so the
         // weight ring gets the depth (up to 5 slots) and the raw A ring keeps 4 tiles
         t.resident = 0;
-        long long nb = (avail - 4 * tile) / slot;  // measured: a 2-tile A ring with one more weight slot is slower
-        if (nb > 5) nb = 5;
+        long long nb = (avail - a_ring_for_streamed() * tile) / slot;  // measured: a 2-tile A ring with one more weight slot is slower
+        if (nb > 6) nb = 6;
         if (nb > (long long)t.n_tiles * t.KB) nb = (long long)t.n_tiles * t.KB;
         if (nb < 2) nb = 2;
         t.nB = (int)nb;
@@ -535,7 +789,195 @@ static bool make_tiling(int K, int N, Tiling& t) {
     return t.smem <= (size_t)SMEM_LIMIT;
 }
 
+constexpr long long DW_BOX_LIMIT = 76 * 1024;
+
+// Depthwise front: TMEM / n-tile geometry as the plain kernel (single n tile only: the depthwise result is not
+// recomputed per n tile), spatial tile = the TH x TW (<= 128 pixels) shape with the least halo + per-tile overhead.
+static bool make_tiling_dw(int K, int N, int S, int Ho, int Wo, Tiling& t) {
+    if (K <= 0 || N <= 0 || K % 8 || N % 4 || (S != 1 && S != 2) || Ho <= 0 || Wo <= 0) return false;
+    t.n_tiles = (N + 191) / 192;
+    if (t.n_tiles != 1) return false;
+    t.BN = (N + 15) / 16 * 16;
+    if (t.BN < 16) t.BN = 16;
+    t.epi_group_bytes = EPI_STAGE_BYTES + (t.BN * 4 + 1023) / 1024 * 1024;
+    t.KB = (K + BK - 1) / BK;
+    t.acc_stride = (t.BN + 31) / 32 * 32;
+    t.nAcc = t.acc_stride <= 64 ? 4 : 2;
+    t.a_col0 = t.nAcc * t.acc_stride;
+    t.nT = (512 - t.a_col0) / T_STAGE_COLS;
+    if (t.nT > MAX_T) t.nT = MAX_T;
+    if (t.nT < 2) return false;
+    // tile = 128 pixels made of 2 x 4 pixel patches (one per converter thread and channel quad)
+    static const int shapes[5][2] = {{8, 16}, {16, 8}, {4, 32}, {32, 4}, {2, 64}};
+    long long best = -1;
+    for (int i = 0; i < 5; ++i) {
+        const int TH = shapes[i][0], TW = shapes[i][1];
+        const int IW = (TW - 1) * S + 3, IH = (TH - 1) * S + 3;
+        if (IW > 256 || IH > 256 || (long long)IW * IH * 128 > DW_BOX_LIMIT) continue;
+        const long long tiles = (long long)((Ho + TH - 1) / TH) * ((Wo + TW - 1) / TW);
+        const long long cost = tiles * ((long long)IW * IH + 96);
+        if (best < 0 || cost < best) {
+            best = cost;
+            t.TH = TH; t.TW = TW; t.IH = IH; t.IW = IW;
+        }
+    }
+    if (best < 0) return false;
+    t.tiles_h = (Ho + t.TH - 1) / t.TH;
+    t.tiles_w = (Wo + t.TW - 1) / t.TW;
+    t.a_slot = (uint32_t)(((long long)t.IW * t.IH * 128 + 1023) / 1024 * 1024);
+    t.b_slot = 2u * t.BN * 128u + DW_TAIL_BYTES;
+    // stride 2: the boxes are ~4x the tile (72 KB each), so one epilogue group gives its transpose buffers up
+    t.epi_groups = t.a_slot > 40 * 1024 ? 1 : 2;
+    const long long fixed = 1024 + (long long)t.epi_groups * t.epi_group_bytes + 2ll * A_TILE_BYTES + BAR_BYTES;  // + 2 staging tiles
+    const long long avail = SMEM_LIMIT - fixed;
+    if (t.KB <= MAX_B && (long long)t.KB * t.b_slot + 2ll * t.a_slot <= avail) {
+        t.resident = 1;
+        t.nB = t.KB;
+    } else {
+        // streamed weights: EVEN ring (a slot then always belongs to the same converter group, which sees every one of
+        // its mbarrier phases - the converters read the depthwise taps from the slot), after two boxes for the A ring
+        t.resident = 0;
+        long long nb = (avail - 2ll * t.a_slot) / t.b_slot;
+        if (t.a_slot <= 32 * 1024 && (avail - 4ll * t.a_slot) / t.b_slot >= 4) nb = (avail - 4ll * t.a_slot) / t.b_slot;
+        if (nb > 6) nb = 6;
+        nb &= ~1ll;
+        if (nb < 2) return false;
+        t.nB = (int)nb;
+    }
+    long long na = (avail - (long long)t.nB * t.b_slot) / t.a_slot;
+    if (na > MAX_A) na = MAX_A;
+    if (na > 6) na = 6;
+    na &= ~1ll;  // even: see make_tiling
+    if (na < 2) return false;
+    t.nA = (int)na;
+    t.smem = (size_t)(fixed + (long long)t.nA * t.a_slot + (long long)t.nB * t.b_slot);
+    return t.smem <= (size_t)SMEM_LIMIT;
+}
+
 }  // namespace ts
+
+// Fused depthwise 3x3 (+BN +act) -> pointwise 1x1 (+BN +act +residual): YR_OP_DWPW.
+int launch_dwpw(const yr_op& op, cudaStream_t s) {
+    YR_CHECK_ARG(op.in && op.out && op.w_tc && op.bias, "dwpw: null pointer (w_tc = yr_dwpw_pack output)");
+    YR_CHECK_ARG(op.k == 3 && (op.stride == 1 || op.stride == 2), "dwpw: depthwise must be 3x3, stride 1 or 2");
+    YR_CHECK_ARG(op.C > 0 && op.C % 8 == 0 && op.N > 0 && op.N % 8 == 0, "dwpw: C=%d N=%d must be multiples of 8", op.C, op.N);
+    YR_CHECK_ARG(op.ld_in >= op.C && op.ld_in % 4 == 0 && op.ld_out >= op.N && op.ld_out % 4 == 0,
+                 "dwpw: bad ld_in=%d ld_out=%d", op.ld_in, op.ld_out);
+    YR_CHECK_ARG(!op.res || (op.ld_res >= op.N && op.ld_res % 4 == 0), "dwpw: bad ld_res=%d", op.ld_res);
+    YR_CHECK_ARG(!op.scale, "dwpw: an SE gate between the depthwise and the pointwise conv cannot be fused");
+    YR_CHECK_ARG(((uintptr_t)op.in | (uintptr_t)op.out | (uintptr_t)op.w_tc | (uintptr_t)op.bias | (uintptr_t)op.res) % 16 == 0,
+                 "dwpw: pointers must be 16-byte aligned");
+    YR_CHECK_ARG(op.B > 0 && op.H > 0 && op.W > 0 && op.Ho > 0 && op.Wo > 0 &&
+                     (long long)op.B * op.Ho * op.Wo * (op.ld_out > op.ld_res ? op.ld_out : op.ld_res) < (1ll << 31),
+                 "dwpw: bad geometry");
+    YR_CHECK_ARG(op.mode >= YR_ACT_NONE && op.mode <= YR_ACT_SWISH, "dwpw: mode = activation of the depthwise conv");
+    ts::Tiling t;
+    if (!ts::make_tiling_dw(op.C, op.N, op.stride, op.Ho, op.Wo, t)) {
+        set_error("dwpw: no tiling for C=%d N=%d stride %d %dx%d", op.C, op.N, op.stride, op.Ho, op.Wo);
+        return YR_ERR_UNSUPPORTED;
+    }
+    tc::EncodeTiledFn enc = tc::encode_tiled();
+    if (!enc) {
+        set_error("dwpw: cuTensorMapEncodeTiled is unavailable in this driver");
+        return YR_ERR_CUDA;
+    }
+    CUtensorMap tm;
+    const cuuint64_t gdim[4] = {(cuuint64_t)op.C, (cuuint64_t)op.W, (cuuint64_t)op.H, (cuuint64_t)op.B};
+    const cuuint64_t gstr[3] = {(cuuint64_t)op.ld_in * 4, (cuuint64_t)op.W * op.ld_in * 4,
+                                (cuuint64_t)op.H * op.W * op.ld_in * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)ts::BK, (cuuint32_t)t.IW, (cuuint32_t)t.IH, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(op.in), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, tc::l2_promotion(),
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        set_error("dwpw: cuTensorMapEncodeTiled failed (%d) for C=%d H=%d W=%d ld=%d box %dx%d", (int)cr, op.C, op.H, op.W,
+                  op.ld_in, t.IW, t.IH);
+        return YR_ERR_CUDA;
+    }
+    ts::Params p = {};
+    p.wp = op.w_tc;
+    p.bias = op.bias;
+    p.res = op.res;
+    p.scale = nullptr;
+    p.out = (float*)op.out;
+    p.M = op.B * t.tiles_h * t.tiles_w * ts::BM;
+    p.K = op.C;
+    p.N = op.N;
+    p.BN = t.BN;
+    p.n_tiles = 1;
+    p.m_tiles = op.B * t.tiles_h * t.tiles_w;
+    p.KB = t.KB;
+    p.ld_out = op.ld_out;
+    p.ld_res = op.ld_res;
+    p.rows_per_img = op.Ho * op.Wo;
+    p.img_w = op.Wo;
+    p.up2 = 0;
+    p.act = op.act;
+    p.nA = t.nA;
+    p.nT = t.nT;
+    p.nB = t.nB;
+    p.nAcc = t.nAcc;
+    p.resident = t.resident;
+    p.acc_stride = t.acc_stride;
+    p.a_col0 = t.a_col0;
+    p.epi_group_bytes = t.epi_group_bytes;
+    p.total_items = p.m_tiles;
+    p.a_slot_bytes = t.a_slot;
+    p.b_slot_bytes = t.b_slot;
+    p.TH = t.TH; p.TW = t.TW; p.IW = t.IW; p.tiles_h = t.tiles_h; p.tiles_w = t.tiles_w;
+    p.Ho = op.Ho; p.Wo = op.Wo; p.pad_t = op.pad_t; p.pad_l = op.pad_l; p.dw_act = op.mode;
+    p.epi_groups = t.epi_groups;
+    p.w_rep = 1;
+    p.w_rep_stride = 0;
+    static DeviceOnce attr_once;  // function attributes are per device
+    bool& attr_set = attr_once.cur();
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(ts::pw_ts_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM_LIMIT) != cudaSuccess ||
+            cudaFuncSetAttribute(ts::pw_ts_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM_LIMIT) != cudaSuccess ||
+            cudaFuncSetAttribute(ts::pw_ts_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM_LIMIT) != cudaSuccess ||
+            cudaFuncSetAttribute(ts::pw_ts_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM_LIMIT) != cudaSuccess) {
+            set_error("dwpw: cannot raise the dynamic shared memory limit: %s", cudaGetErrorString(cudaGetLastError()));
+            return YR_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    const int max_ctas = tc::num_sms();
+    p.items_per_cta = (p.total_items + max_ctas - 1) / max_ctas;
+    const int grid = (p.total_items + p.items_per_cta - 1) / p.items_per_cta;
+    p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(t.BN >> 3) << 17) | ((uint32_t)(ts::BM >> 4) << 24);
+    p.dbg = nullptr;
+    static const bool debug = getenv("YR_PW_TC_DEBUG") != nullptr;  // developer aid only: timeline of CTA 0
+    if (debug) {
+        static long long* dbuf = nullptr;
+        if (!dbuf) cudaMalloc(&dbuf, 8 * ts::DBG_EV * sizeof(long long));
+        cudaMemsetAsync(dbuf, 0, 8 * ts::DBG_EV * sizeof(long long), s);
+        p.dbg = dbuf;
+    }
+    auto kern = op.stride == 1 ? (debug ? ts::pw_ts_kernel<true, 1> : ts::pw_ts_kernel<false, 1>)
+                               : (debug ? ts::pw_ts_kernel<true, 2> : ts::pw_ts_kernel<false, 2>);
+    if (launch_pdl(kern, dim3(grid), dim3(ts::NUM_THREADS), t.smem, s, tm, p) != cudaSuccess) {
+        set_error("dwpw: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return YR_ERR_CUDA;
+    }
+    if (debug) {
+        static long long h[8 * ts::DBG_EV];
+        cudaStreamSynchronize(s);
+        cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        const char* names[8] = {"tma_issue", "a_full_seen", "t_empty_seen", "conv_done", "mma_start", "mma_issued",
+                                "acc_full_seen", "epi_done"};
+        long long t0 = h[0];
+        fprintf(stderr, "dwpw timeline C=%d N=%d s%d %dx%d tile %dx%d box %dx%d tiles %dx%d BN=%d KB=%d nA=%d nT=%d nB=%d nAcc=%d resident=%d items/cta=%d grid=%d smem=%zu\n",
+                p.K, p.N, op.stride, op.Ho, op.Wo, t.TH, t.TW, t.IH, t.IW, t.tiles_h, t.tiles_w, p.BN, p.KB, p.nA, p.nT, p.nB,
+                p.nAcc, p.resident, p.items_per_cta, grid, t.smem);
+        for (int r = 0; r < 8; ++r) {
+            fprintf(stderr, "%-14s", names[r]);
+            for (int i = 0; i < 40 && h[r * ts::DBG_EV + i]; ++i) fprintf(stderr, " %6lld", h[r * ts::DBG_EV + i] - t0);
+            fprintf(stderr, "\n");
+        }
+    }
+    return YR_OK;
+}
 
 int launch_pw_ts(const yr_op& op, cudaStream_t s) {
     YR_CHECK_ARG(op.in && op.out && op.w_tc && op.bias, "pw_ts: null pointer (w_tc = yr_pw_ts_pack output)");
@@ -601,12 +1043,19 @@ int launch_pw_ts(const yr_op& op, cudaStream_t s) {
     p.a_col0 = t.a_col0;
     p.epi_group_bytes = t.epi_group_bytes;
     p.total_items = p.n_tiles * p.m_tiles;
+    p.a_slot_bytes = ts::A_TILE_BYTES;
+    p.b_slot_bytes = 2u * t.BN * 128u;
+    p.TH = p.TW = p.IW = p.tiles_h = p.tiles_w = 1;
+    p.Ho = p.Wo = p.pad_t = p.pad_l = p.dw_act = 0;
+    p.epi_groups = 2;
+    p.w_rep = t.resident ? 1 : ts::weight_replicas();
+    p.w_rep_stride = (size_t)t.n_tiles * t.KB * 2 * t.BN * ts::BK * 4;
     static DeviceOnce attr_once;  // function attributes are per device
     bool& attr_set = attr_once.cur();
     if (!attr_set) {
-        if (cudaFuncSetAttribute(ts::pw_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM_LIMIT) !=
+        if (cudaFuncSetAttribute(ts::pw_ts_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM_LIMIT) !=
                 cudaSuccess ||
-            cudaFuncSetAttribute(ts::pw_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM_LIMIT) !=
+            cudaFuncSetAttribute(ts::pw_ts_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM_LIMIT) !=
                 cudaSuccess) {
             set_error("pw_ts: cannot raise the dynamic shared memory limit: %s", cudaGetErrorString(cudaGetLastError()));
             return YR_ERR_CUDA;
@@ -628,7 +1077,7 @@ int launch_pw_ts(const yr_op& op, cudaStream_t s) {
         cudaMemsetAsync(dbuf, 0, 8 * ts::DBG_EV * sizeof(long long), s);
         p.dbg = dbuf;
     }
-    if (launch_pdl(debug ? ts::pw_ts_kernel<true> : ts::pw_ts_kernel<false>, dim3(grid), dim3(ts::NUM_THREADS), t.smem, s, tm,
+    if (launch_pdl(debug ? ts::pw_ts_kernel<true, 0> : ts::pw_ts_kernel<false, 0>, dim3(grid), dim3(ts::NUM_THREADS), t.smem, s, tm,
                    p) != cudaSuccess) {
         set_error("pw_ts: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         return YR_ERR_CUDA;
@@ -658,7 +1107,7 @@ using namespace yr;
 extern "C" int64_t yr_pw_ts_packed_floats(int K, int N) {
     ts::Tiling t;
     if (!ts::make_tiling(K, N, t)) return 0;
-    return (int64_t)t.n_tiles * t.KB * 2 * t.BN * ts::BK;
+    return (int64_t)t.n_tiles * t.KB * 2 * t.BN * ts::BK * (t.resident ? 1 : ts::weight_replicas());
 }
 
 extern "C" int yr_pw_ts_pack(const float* w, int K, int N, float* packed, void* stream) {
@@ -670,7 +1119,45 @@ extern "C" int yr_pw_ts_pack(const float* w, int K, int N, float* packed, void* 
     }
     YR_CHECK_ARG(((uintptr_t)packed) % 128 == 0, "pw_ts_pack: packed must be 128-byte aligned");
     const long long total = (long long)t.n_tiles * t.KB * t.BN * ts::BK;
-    ts::pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, K, N, t.BN, t.n_tiles, t.KB, packed);
+    const int reps = t.resident ? 1 : ts::weight_replicas();
+    for (int r = 0; r < reps; ++r)
+        ts::pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, K, N, t.BN, t.n_tiles, t.KB,
+                                                                                            packed + (size_t)r * 2 * total, 0);
     YR_CHECK_LAUNCH("pw_ts_pack");
     return YR_OK;
+}
+
+// Weight image of a fused depthwise -> pointwise pair (YR_OP_DWPW): per 32-channel k-block the pointwise (hi | lo)
+// TF32 tiles of yr_pw_ts_pack followed by that k-block's depthwise taps [9][32] and biases [32] (BN folded).
+// The image depends on N and K only (not on the spatial size).
+extern "C" int64_t yr_dwpw_packed_floats(int K, int N) {
+    ts::Tiling t;
+    if (!ts::make_tiling_dw(K, N, 1, 8, 16, t)) return 0;
+    return (int64_t)t.KB * (2 * t.BN * ts::BK + ts::DW_TAIL_BYTES / 4);
+}
+
+extern "C" int yr_dwpw_pack(const float* w_pw, int K, int N, const float* w_dw, const float* b_dw, float* packed,
+                            void* stream) {
+    YR_CHECK_ARG(w_pw && w_dw && b_dw && packed, "dwpw_pack: null pointer");
+    ts::Tiling t;
+    if (!ts::make_tiling_dw(K, N, 1, 8, 16, t)) {
+        set_error("dwpw_pack: no fused tiling for K=%d N=%d", K, N);
+        return YR_ERR_UNSUPPORTED;
+    }
+    YR_CHECK_ARG(((uintptr_t)packed) % 128 == 0, "dwpw_pack: packed must be 128-byte aligned");
+    const int tail = ts::DW_TAIL_BYTES / 4;
+    const long long total = (long long)t.KB * t.BN * ts::BK;
+    ts::pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w_pw, K, N, t.BN, 1, t.KB, packed, tail);
+    YR_CHECK_LAUNCH("dwpw_pack");
+    const int n2 = t.KB * tail;
+    ts::pack_dw_tail_kernel<<<(n2 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        w_dw, b_dw, K, t.KB, (size_t)2 * t.BN * ts::BK + tail, (size_t)2 * t.BN * ts::BK, packed);
+    YR_CHECK_LAUNCH("dwpw_pack");
+    return YR_OK;
+}
+
+/* 1 when (C, N, stride, Ho, Wo) has a fused depthwise->pointwise tiling, else 0 (the engine then runs the two ops). */
+extern "C" int yr_dwpw_supported(int C, int N, int stride, int Ho, int Wo) {
+    ts::Tiling t;
+    return ts::make_tiling_dw(C, N, stride, Ho, Wo, t) ? 1 : 0;
 }

@@ -62,7 +62,7 @@ class Engine:
                  num_scales: int = 3, max_boxes: int = 20, cand_cap: Optional[int] = None,
                  device: Optional[torch.device] = None, pw_variant: int = _lib.PW_AUTO, input_u8: bool = False,
                  fuse_se: bool = True, fuse_mbconv: bool = False, lanes: int = 1, autotune: bool = True, fuse_up2: bool = True,
-                 num_anchors: int = 3):
+                 num_anchors: int = 3, fuse_dwpw: bool = True):
         if not torch.cuda.is_available():
             raise _lib.YrError("yoloret_b200.Engine needs a CUDA device (no CPU fallback exists)")
         self.lib = _lib.lib()
@@ -73,10 +73,10 @@ class Engine:
             self.device = torch.device("cuda", torch.cuda.current_device())
         with torch.cuda.device(self.device):  # allocations, attribute caches and the autotuner run on that GPU
             self._init(model_name, num_classes, input_hw, batch, weights, anchors, micro_batch, num_scales, max_boxes,
-                       cand_cap, pw_variant, input_u8, fuse_se, fuse_mbconv, lanes, autotune, fuse_up2, num_anchors)
+                       cand_cap, pw_variant, input_u8, fuse_se, fuse_mbconv, lanes, autotune, fuse_up2, num_anchors, fuse_dwpw)
 
     def _init(self, model_name, num_classes, input_hw, batch, weights, anchors, micro_batch, num_scales, max_boxes,
-              cand_cap, pw_variant, input_u8, fuse_se, fuse_mbconv, lanes, autotune, fuse_up2, num_anchors):
+              cand_cap, pw_variant, input_u8, fuse_se, fuse_mbconv, lanes, autotune, fuse_up2, num_anchors, fuse_dwpw=True):
         # the reference derives anchors per scale as num_anchors // num_scales (code/yolo.py:214-216); decode, the head
         # width and the y_true layout of this engine are written for 3 per scale (every shipped anchor file: 9 / 3)
         if int(num_anchors) != 3:
@@ -102,6 +102,7 @@ class Engine:
         self.fuse_mbconv = fuse_mbconv
         self.autotune = bool(autotune)
         self.fuse_up2 = bool(fuse_up2)
+        self.fuse_dwpw = bool(fuse_dwpw)
         self.cand_cap_arg = cand_cap
         self._check_weights(weights)
         self._alloc()
@@ -205,6 +206,7 @@ class Engine:
                 mat = _pad_cols(np.concatenate(mats, 0), L.out.C)
                 self.wdev[i] = (self._dev(mat), self._dev(w["weighted_sum/alpha"]))
         self._find_fused_blocks()
+        self._find_dwpw_pairs()
         torch.cuda.synchronize(self.device)
         self.weight_bytes = sum(a.numel() * 4 + b.numel() * 4 for a, b in self.wdev.values())
 
@@ -246,6 +248,51 @@ class Engine:
                        "yr_mbconv_pack")
             self.mb_blob[i] = blob
 
+    def _layer_consumers(self) -> Dict[str, int]:
+        if getattr(self, "_consumers", None) is None:
+            self._consumers = {}
+            for L in self.net.layers:
+                for v in L.inp + ([L.res] if L.res is not None else []):
+                    self._consumers[v.buf.name] = self._consumers.get(v.buf.name, 0) + 1
+        return self._consumers
+
+    def _find_dwpw_pairs(self):
+        """3x3 depthwise conv (+BN +act) directly followed by the 1x1 conv that is its only reader - block_N_depthwise ->
+        block_N_project of MobileNetV2 (reference code/yolo3/override.py:339-341), the SE-less MBConv blocks of
+        EfficientNet-lite (code/yolo3/efficientnet.py:501-533) - run as ONE yr_op (YR_OP_DWPW): the depthwise result goes
+        from the converter warps' registers straight into tensor memory as the GEMM's A operand, so the widest tensor
+        of the block is written to HBM once (by the expand conv) and read once, instead of twice each.  Bit-identical to
+        the two separate ops (tests/test_gpu_ops.py).  Pairs with an SE gate in between, 5x5 depthwise kernels or more
+        than 192 output channels keep the separate kernels."""
+        self.dwpw_blob: Dict[int, torch.Tensor] = {}
+        if not self.fuse_dwpw or self.pw_variant == _lib.PW_SIMT:
+            return
+        Ls = self.net.layers
+        cons = self._layer_consumers()
+        for i in range(len(Ls) - 1):
+            d, b = Ls[i], Ls[i + 1]
+            if i in self.mb_blob or (i - 1) in self.mb_blob:
+                continue
+            ok = (d.kind == "dw" and d.k == 3 and d.stride in (1, 2) and b.kind == "pw" and b.gate is None
+                  and b.inp[0].buf is d.out.buf and b.inp[0].off == d.out.off and b.inp[0].C == d.out.C
+                  and cons.get(d.out.buf.name, 0) == 1 and not d.out.buf.full_batch and not self.se_fused.get(i + 1)
+                  and not self._up2_fused_into(i + 1))
+            if not ok:
+                continue
+            C_, N_ = d.out.C, b.out.C
+            if not self.lib.yr_dwpw_supported(C_, N_, d.stride, d.out.H, d.out.W):
+                continue
+            n = int(self.lib.yr_dwpw_packed_floats(C_, N_))
+            if n <= 0:
+                continue
+            blob = torch.zeros(n, dtype=torch.float32, device=self.device)
+            wd, bd = self.wdev[i]
+            wp, _bp = self.wdev[i + 1]
+            assert int(wd.shape[1]) == C_ and tuple(wp.shape) == (C_, N_), (wd.shape, wp.shape, C_, N_)
+            _lib.check(self.lib.yr_dwpw_pack(wp.data_ptr(), C_, N_, wd.data_ptr(), bd.data_ptr(), blob.data_ptr(),
+                                             self._stream()), "yr_dwpw_pack")
+            self.dwpw_blob[i] = blob
+
     def _pack_tc(self, w_kn: torch.Tensor, variant: int) -> Optional[torch.Tensor]:
         """yr_pw_tc_pack / yr_pw_ts_pack: [K,N] fp32 -> split/swizzled TF32 (hi, lo) image for a tcgen05 kernel."""
         K, N = int(w_kn.shape[0]), int(w_kn.shape[1])
@@ -272,12 +319,7 @@ class Engine:
             return False
         if not (r.inp[0].buf is a.out.buf and r.inp[0].off == a.out.off and r.inp[0].C == a.out.C):
             return False
-        if getattr(self, "_consumers", None) is None:
-            self._consumers = {}
-            for L in Ls:
-                for v in L.inp + ([L.res] if L.res is not None else []):
-                    self._consumers[v.buf.name] = self._consumers.get(v.buf.name, 0) + 1
-        if self._consumers.get(a.out.buf.name, 0) != 1 or a.out.buf.full_batch:
+        if self._layer_consumers().get(a.out.buf.name, 0) != 1 or a.out.buf.full_batch:
             return False
         return self._pw_variant_of(i) in (_lib.PW_TC, _lib.PW_TS) and i not in self.mb_blob and (i - 2) not in self.mb_blob
 
@@ -400,6 +442,27 @@ class Engine:
                     + self.mb_blob[i].numel() * 4
                 meta.append(("mbconv", L.name.replace("_expand", "") + "_fused", fused_bytes, L.flops + d.flops + b.flops, i))
                 skip = 2
+                continue
+            if i in self.dwpw_blob:
+                b = self.net.layers[i + 1]
+                o.kind = _lib.OP_DWPW
+                o.B, o.H, o.W, o.C = nb, x.H, x.W, x.C
+                o.Ho, o.Wo, o.N = b.out.H, b.out.W, b.out.C
+                o.k, o.stride = 3, L.stride
+                o.pad_t, o.pad_l = L.extra.get("pad_t", 0), L.extra.get("pad_l", 0)
+                o.mode, o.act = _ACT[L.act], _ACT[b.act]
+                o.ld_in, o.ld_out = x.buf.ld, b.out.buf.ld
+                o.in_ = _ptr(x, chunk0, slot)
+                o.out = _ptr(b.out, chunk0)
+                o.w_tc = self.dwpw_blob[i].data_ptr()
+                o.bias = self.wdev[i + 1][1].data_ptr()
+                if b.res is not None:
+                    o.res, o.ld_res = _ptr(b.res, chunk0), b.res.buf.ld
+                # algorithmic bytes of the fused pair: depthwise input + 1x1 output (+ residual) + both layers' weights
+                fused_bytes = 4 * (x.H * x.W * x.Clog + b.out.H * b.out.W * b.out.Clog * (2 if b.res is not None else 1)
+                                   + (L.k * L.k + 2) * x.Clog + x.Clog * b.out.Clog + 2 * b.out.Clog)
+                meta.append(("dwpw", L.name + "+" + b.name.split("_")[-1], fused_bytes, L.flops + b.flops, i))
+                skip = 1
                 continue
             meta.append((L.kind, L.name, L.bytes_alg, L.flops, i))
             o.act = _ACT[L.act]
