@@ -264,6 +264,50 @@ int yr_yolo_loss(const float* logits, const float* y_true, const float* true_box
                  const yr_loss_params* p, float* loss_parts, float* dlogits, void* workspace,
                  int64_t workspace_bytes, void* stream);
 
+/* ---- training, fast path: sparse y_true + the loss of ALL scales in one launch --------------------------
+ * Replaces the same reference code as yr_encode_true_boxes + num_scales x yr_yolo_loss (preprocess_true_boxes,
+ * code/yolo3/utils.py:298-376; YoloLoss.call, code/yolo3/model.py:607-671; the sum over scales, code/yolo3/train.py:11-16)
+ * without materialising the dense y_true tensors (> 99.9 % zeros) - SURVEY.md section 8f-2.
+ *
+ * Sparse y_true of a batch:
+ *   slot_maps[l]  int32 [B][gh_l][gw_l][3]: index of the slot's record in scale l's record list, or -1
+ *   records       float [3][max_records][8]: (x, y, w, h) normalised centre form = y_true[..., 0:4], then 4 words of
+ *                 class bits (bit c of word c / 32 = y_true[..., 5 + c]); num_classes <= 128
+ *   counts        int32 [3]: records per scale (max_records >= B * T can never overflow)
+ * yr_encode_true_boxes_sparse takes the same inputs as yr_encode_true_boxes and fills the three (it clears the
+ * maps and counts itself).  slot_maps is a HOST array of DEVICE pointers; anchors a HOST pointer to 9 (w, h) pairs.
+ *
+ * yr_yolo_loss3: logits[l] / dlogits[l] [B][gh_l][gw_l][ld_logits[l]] (3 anchors x (5 + C) values per cell; HOST
+ * arrays of DEVICE pointers, dlogits may be NULL for forward only).
+ *   loss_parts [3][4]: per scale giou, confidence, class sums (already / B) and sum(ignore_mask); the reference's loss
+ *                      is the sum of the first three over the scales.
+ *   workspace  >= yr_yolo_loss3_workspace(p) bytes, ZEROED once before the first call (it holds the arrival counter
+ *              the kernel re-arms itself); one launch, no host synchronisation, CUDA-graph capturable. */
+typedef struct yr_loss3_params {
+    int32_t B, C, num_scales;
+    int32_t gh[3], gw[3], ld_logits[3];
+    float anchors[3][3][2]; /* per scale, the 3 anchors (w, h) in input pixels: anchors[anchor_mask[l][k]] */
+    int32_t input_h, input_w;
+    float ignore_thresh;
+    int32_t max_records;
+} yr_loss3_params;
+
+int yr_encode_true_boxes_sparse(const float* boxes, int B, int T, const float* anchors, int input_h, int input_w,
+                                int num_classes, int num_scales, int32_t* const* slot_maps, float* records,
+                                int32_t* counts, int max_records, void* stream);
+int64_t yr_yolo_loss3_workspace(const yr_loss3_params* p);
+int yr_yolo_loss3(const float* const* logits, const int32_t* const* slot_maps, const float* records,
+                  const int32_t* counts, const yr_loss3_params* p, float* loss_parts, float* const* dlogits,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- training: optimizer step (reference code/train.py:158-160,195-197: tf.keras.optimizers.Adam(lr, epsilon=1e-8)) ---
+ * In-place Adam update of a flat fp32 parameter vector (or a rank's shard of it) with TF's ApplyAdam arithmetic:
+ *   alpha = lr * sqrt(1 - beta2^step) / (1 - beta1^step);  m += (g - m)(1 - beta1);  v += (g*g - v)(1 - beta2);
+ *   param -= (m * alpha) / (sqrt(v) + epsilon).     step is 1-based.  lr comes from the host (epoch-wise CosineDecay,
+ * code/train.py:92-100: yoloret_b200.train.cosine_decay). */
+int yr_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                 float epsilon, int64_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,16 @@ class YrLossParams(C.Structure):
     ]
 
 
+class YrLoss3Params(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("C", C.c_int32), ("num_scales", C.c_int32),
+        ("gh", C.c_int32 * 3), ("gw", C.c_int32 * 3), ("ld_logits", C.c_int32 * 3),
+        ("anchors", ((C.c_float * 2) * 3) * 3),
+        ("input_h", C.c_int32), ("input_w", C.c_int32),
+        ("ignore_thresh", C.c_float), ("max_records", C.c_int32),
+    ]
+
+
 # every symbol the header declares: (name, restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -85,6 +95,12 @@ SYMBOLS = {
     "yr_yolo_loss_workspace": (C.c_int64, [C.POINTER(YrLossParams)]),
     "yr_yolo_loss_gather_true": (C.c_int, [_P, C.POINTER(YrLossParams), _P, _P, _P]),
     "yr_yolo_loss": (C.c_int, [_P, _P, _P, _P, C.POINTER(YrLossParams), _P, _P, _P, C.c_int64, _P]),
+    "yr_encode_true_boxes_sparse": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int,
+                                              C.POINTER(_P), _P, _P, C.c_int, _P]),
+    "yr_yolo_loss3_workspace": (C.c_int64, [C.POINTER(YrLoss3Params)]),
+    "yr_yolo_loss3": (C.c_int, [C.POINTER(_P), C.POINTER(_P), _P, _P, C.POINTER(YrLoss3Params), _P, C.POINTER(_P), _P,
+                                C.c_int64, _P]),
+    "yr_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, _P]),
     "yr_encode_true_boxes": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.POINTER(_P), _P]),
 }

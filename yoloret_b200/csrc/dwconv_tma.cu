@@ -134,11 +134,7 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tm, const Params p) {
                         const float4 ww = w[kh * KS + kw];
 #pragma unroll
                         for (int o = 0; o < PW; ++o) {
-                            const float4 xv = x[o * S + kw];
-                            acc[t][o].x = fmaf(xv.x, ww.x, acc[t][o].x);
-                            acc[t][o].y = fmaf(xv.y, ww.y, acc[t][o].y);
-                            acc[t][o].z = fmaf(xv.z, ww.z, acc[t][o].z);
-                            acc[t][o].w = fmaf(xv.w, ww.w, acc[t][o].w);
+                            fma4(acc[t][o], x[o * S + kw], ww);
                         }
                     }
                 }

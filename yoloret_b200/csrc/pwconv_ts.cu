@@ -75,8 +75,6 @@ struct Params {
     uint32_t a_slot_bytes, b_slot_bytes;  // ring slot sizes (depthwise front: halo'd box / weight slot + dw taps)
     // depthwise front: spatial tiling of the output (an item = one TH x TW tile of one image)
     int TH, TW, IW, tiles_h, tiles_w, Ho, Wo, pad_t, pad_l, dw_act;
-    int w_rep;             // copies of the weight image in global memory (CTA i streams copy i % w_rep)
-    size_t w_rep_stride;   // bytes between copies
     int epi_groups;  // 2 (the groups alternate tiles) or 1 (stride-2 depthwise front: shared memory goes to the boxes)
     long long* dbg;
 };
@@ -339,7 +337,9 @@ __device__ __forceinline__ void dw_converter_loop(const Params& p, const uint8_t
     const int pg = gtid >> 3;                 // phase 1: pixel patch
     const int gw = p.TW / PW;
     const int gx = pg % gw, gy = pg / gw;
-    const int box_off = ((gy * PH * S) * p.IW + gx * PW * S) * BK + cq * 4;  // floats
+    const bool worker = gy * PH < p.TH;       // tiles of fewer than 128 pixels leave the last patches / rows idle
+    const bool live_row = gtid < p.TH * p.TW;
+    const int box_off = worker ? ((gy * PH * S) * p.IW + gx * PW * S) * BK + cq * 4 : 0;  // floats
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)p.a_col0;
     const uint32_t dw_off = 2u * p.BN * 128u;
     const uint32_t bar_id = 3u + (uint32_t)grp;
@@ -367,6 +367,7 @@ __device__ __forceinline__ void dw_converter_loop(const Params& p, const uint8_t
                 for (int t = 0; t < PH; ++t)
 #pragma unroll
                     for (int o = 0; o < PW; ++o) acc[t][o] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (worker) {
 #pragma unroll
                 for (int rr = 0; rr < IN_ROWS; ++rr) {
                     float4 x[IN_COLS];
@@ -382,20 +383,18 @@ __device__ __forceinline__ void dw_converter_loop(const Params& p, const uint8_t
                             const float4 ww = wd[(kh * KS + kw) * 8];
 #pragma unroll
                             for (int o = 0; o < PW; ++o) {
-                                const float4 xv = x[o * S + kw];
-                                acc[t][o].x = fmaf(xv.x, ww.x, acc[t][o].x);
-                                acc[t][o].y = fmaf(xv.y, ww.y, acc[t][o].y);
-                                acc[t][o].z = fmaf(xv.z, ww.z, acc[t][o].z);
-                                acc[t][o].w = fmaf(xv.w, ww.w, acc[t][o].w);
+                                fma4(acc[t][o], x[o * S + kw], ww);
                             }
                         }
                     }
+                }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar0 + 8u * (BAR_A_EMPTY + ra.slot));  // this warp is done with the box
                 const float4 bv = wd[72];
                 // the staging tile may still be read by phase 2 of this group's previous k-block
                 asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                if (worker) {
 #pragma unroll
                 for (int t = 0; t < PH; ++t) {
 #pragma unroll
@@ -409,13 +408,16 @@ __device__ __forceinline__ void dw_converter_loop(const Params& p, const uint8_t
                         *reinterpret_cast<float4*>(stage + r * BK + ((cq ^ (r & 7)) << 2)) = v;
                     }
                 }
+                }
                 asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                 // ---- phase 2: row gtid of the staging tile -> (hi, lo) TF32 columns of the TMEM stage ----
                 float4 v[8];
                 {
                     const float* rowp = stage + gtid * BK;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(rowp + ((c ^ (gtid & 7)) << 2));
+                    for (int c = 0; c < 8; ++c)
+                        v[c] = live_row ? *reinterpret_cast<const float4*>(rowp + ((c ^ (gtid & 7)) << 2))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 mbar_wait(bar0 + 8u * (BAR_T_EMPTY + rt.slot), rt.phase ^ 1u, 7);
                 tc_fence_after();
@@ -548,7 +550,7 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
         if (lane == 0) {
             Ring rb;
             int nt = item0 % p.n_tiles;
-            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wp) + (size_t)(blockIdx.x % (unsigned)p.w_rep) * p.w_rep_stride;
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wp);
             if (p.resident) {  // the whole weight image once, first-needed slots first
                 const int total = p.n_tiles * p.KB;
                 for (int i = 0; i < total; ++i) {
@@ -718,16 +720,6 @@ __global__ void pack_dw_tail_kernel(const float* __restrict__ w_dw, const float*
     packed[(size_t)kb * slot_floats + tail_off + e] = v;
 }
 
-// Copies of a streamed weight image: every SM streams the SAME image from L2 for every row block, so its lines are hot
-// spots of a few L2 slices; copy i % R at a different address spreads the load (experiment knob YR_PW_WREP, default 1).
-inline int weight_replicas() {
-    static const int v = [] {
-        const char* e = getenv("YR_PW_WREP");
-        const int r = e ? atoi(e) : 1;
-        return r >= 1 && r <= 16 ? r : 1;
-    }();
-    return v;
-}
 inline int a_ring_for_streamed() {  // experiment knob YR_PW_STREAM_NA: raw A tiles kept when weights are streamed
     static const int v = [] {
         const char* e = getenv("YR_PW_STREAM_NA");
@@ -807,51 +799,56 @@ static bool make_tiling_dw(int K, int N, int S, int Ho, int Wo, Tiling& t) {
     t.nT = (512 - t.a_col0) / T_STAGE_COLS;
     if (t.nT > MAX_T) t.nT = MAX_T;
     if (t.nT < 2) return false;
-    // tile = 128 pixels made of 2 x 4 pixel patches (one per converter thread and channel quad)
-    static const int shapes[5][2] = {{8, 16}, {16, 8}, {4, 32}, {32, 4}, {2, 64}};
+    // tile = up to 128 pixels made of 2 x 4 pixel patches (one per converter thread and channel quad); the 64-pixel
+    // shapes are the fallback when the boxes of a full tile leave no room for the weight slots (stride 2, wide layers)
+    static const int shapes[9][2] = {{8, 16}, {16, 8}, {4, 32}, {32, 4}, {2, 64}, {4, 16}, {8, 8}, {16, 4}, {2, 32}};
     long long best = -1;
-    for (int i = 0; i < 5; ++i) {
+    Tiling bt = t;
+    for (int i = 0; i < 9; ++i) {
+        Tiling c = t;
         const int TH = shapes[i][0], TW = shapes[i][1];
-        const int IW = (TW - 1) * S + 3, IH = (TH - 1) * S + 3;
-        if (IW > 256 || IH > 256 || (long long)IW * IH * 128 > DW_BOX_LIMIT) continue;
+        c.TH = TH; c.TW = TW;
+        c.IW = (TW - 1) * S + 3; c.IH = (TH - 1) * S + 3;
+        if (c.IW > 256 || c.IH > 256 || (long long)c.IW * c.IH * 128 > DW_BOX_LIMIT) continue;
+        c.a_slot = (uint32_t)(((long long)c.IW * c.IH * 128 + 1023) / 1024 * 1024);
+        c.b_slot = 2u * c.BN * 128u + DW_TAIL_BYTES;
+        // stride 2: the boxes are ~4x the tile, so one epilogue group gives its transpose buffers up
+        c.epi_groups = c.a_slot > 40 * 1024 ? 1 : 2;
+        const long long fixed = 1024 + (long long)c.epi_groups * c.epi_group_bytes + 2ll * A_TILE_BYTES + BAR_BYTES;  // + 2 staging tiles
+        const long long avail = SMEM_LIMIT - fixed;
+        if (c.KB <= MAX_B && (long long)c.KB * c.b_slot + 2ll * c.a_slot <= avail) {
+            c.resident = 1;
+            c.nB = c.KB;
+        } else {
+            // streamed weights: EVEN ring (a slot then always belongs to the same converter group, which sees every one
+            // of its mbarrier phases - the converters read the depthwise taps from the slot), after two boxes for the A ring
+            c.resident = 0;
+            long long nb = (avail - 2ll * c.a_slot) / c.b_slot;
+            if (c.a_slot <= 32 * 1024 && (avail - 4ll * c.a_slot) / c.b_slot >= 4) nb = (avail - 4ll * c.a_slot) / c.b_slot;
+            if (nb > 6) nb = 6;
+            nb &= ~1ll;
+            if (nb < 2) continue;
+            c.nB = (int)nb;
+        }
+        long long na = (avail - (long long)c.nB * c.b_slot) / c.a_slot;
+        if (na > 6) na = 6;
+        na &= ~1ll;  // even: see make_tiling
+        if (na < 2) continue;
+        c.nA = (int)na;
+        c.smem = (size_t)(fixed + (long long)c.nA * c.a_slot + (long long)c.nB * c.b_slot);
+        if (c.smem > (size_t)SMEM_LIMIT) continue;
         const long long tiles = (long long)((Ho + TH - 1) / TH) * ((Wo + TW - 1) / TW);
-        const long long cost = tiles * ((long long)IW * IH + 96);
+        const long long cost = tiles * ((long long)c.IW * c.IH + 96);
         if (best < 0 || cost < best) {
             best = cost;
-            t.TH = TH; t.TW = TW; t.IH = IH; t.IW = IW;
+            bt = c;
         }
     }
     if (best < 0) return false;
+    t = bt;
     t.tiles_h = (Ho + t.TH - 1) / t.TH;
     t.tiles_w = (Wo + t.TW - 1) / t.TW;
-    t.a_slot = (uint32_t)(((long long)t.IW * t.IH * 128 + 1023) / 1024 * 1024);
-    t.b_slot = 2u * t.BN * 128u + DW_TAIL_BYTES;
-    // stride 2: the boxes are ~4x the tile (72 KB each), so one epilogue group gives its transpose buffers up
-    t.epi_groups = t.a_slot > 40 * 1024 ? 1 : 2;
-    const long long fixed = 1024 + (long long)t.epi_groups * t.epi_group_bytes + 2ll * A_TILE_BYTES + BAR_BYTES;  // + 2 staging tiles
-    const long long avail = SMEM_LIMIT - fixed;
-    if (t.KB <= MAX_B && (long long)t.KB * t.b_slot + 2ll * t.a_slot <= avail) {
-        t.resident = 1;
-        t.nB = t.KB;
-    } else {
-        // streamed weights: EVEN ring (a slot then always belongs to the same converter group, which sees every one of
-        // its mbarrier phases - the converters read the depthwise taps from the slot), after two boxes for the A ring
-        t.resident = 0;
-        long long nb = (avail - 2ll * t.a_slot) / t.b_slot;
-        if (t.a_slot <= 32 * 1024 && (avail - 4ll * t.a_slot) / t.b_slot >= 4) nb = (avail - 4ll * t.a_slot) / t.b_slot;
-        if (nb > 6) nb = 6;
-        nb &= ~1ll;
-        if (nb < 2) return false;
-        t.nB = (int)nb;
-    }
-    long long na = (avail - (long long)t.nB * t.b_slot) / t.a_slot;
-    if (na > MAX_A) na = MAX_A;
-    if (na > 6) na = 6;
-    na &= ~1ll;  // even: see make_tiling
-    if (na < 2) return false;
-    t.nA = (int)na;
-    t.smem = (size_t)(fixed + (long long)t.nA * t.a_slot + (long long)t.nB * t.b_slot);
-    return t.smem <= (size_t)SMEM_LIMIT;
+    return true;
 }
 
 }  // namespace ts
@@ -928,8 +925,6 @@ int launch_dwpw(const yr_op& op, cudaStream_t s) {
     p.TH = t.TH; p.TW = t.TW; p.IW = t.IW; p.tiles_h = t.tiles_h; p.tiles_w = t.tiles_w;
     p.Ho = op.Ho; p.Wo = op.Wo; p.pad_t = op.pad_t; p.pad_l = op.pad_l; p.dw_act = op.mode;
     p.epi_groups = t.epi_groups;
-    p.w_rep = 1;
-    p.w_rep_stride = 0;
     static DeviceOnce attr_once;  // function attributes are per device
     bool& attr_set = attr_once.cur();
     if (!attr_set) {
@@ -1048,8 +1043,6 @@ int launch_pw_ts(const yr_op& op, cudaStream_t s) {
     p.TH = p.TW = p.IW = p.tiles_h = p.tiles_w = 1;
     p.Ho = p.Wo = p.pad_t = p.pad_l = p.dw_act = 0;
     p.epi_groups = 2;
-    p.w_rep = t.resident ? 1 : ts::weight_replicas();
-    p.w_rep_stride = (size_t)t.n_tiles * t.KB * 2 * t.BN * ts::BK * 4;
     static DeviceOnce attr_once;  // function attributes are per device
     bool& attr_set = attr_once.cur();
     if (!attr_set) {
@@ -1107,7 +1100,7 @@ using namespace yr;
 extern "C" int64_t yr_pw_ts_packed_floats(int K, int N) {
     ts::Tiling t;
     if (!ts::make_tiling(K, N, t)) return 0;
-    return (int64_t)t.n_tiles * t.KB * 2 * t.BN * ts::BK * (t.resident ? 1 : ts::weight_replicas());
+    return (int64_t)t.n_tiles * t.KB * 2 * t.BN * ts::BK;
 }
 
 extern "C" int yr_pw_ts_pack(const float* w, int K, int N, float* packed, void* stream) {
@@ -1119,10 +1112,7 @@ extern "C" int yr_pw_ts_pack(const float* w, int K, int N, float* packed, void* 
     }
     YR_CHECK_ARG(((uintptr_t)packed) % 128 == 0, "pw_ts_pack: packed must be 128-byte aligned");
     const long long total = (long long)t.n_tiles * t.KB * t.BN * ts::BK;
-    const int reps = t.resident ? 1 : ts::weight_replicas();
-    for (int r = 0; r < reps; ++r)
-        ts::pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, K, N, t.BN, t.n_tiles, t.KB,
-                                                                                            packed + (size_t)r * 2 * total, 0);
+    ts::pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, K, N, t.BN, t.n_tiles, t.KB, packed, 0);
     YR_CHECK_LAUNCH("pw_ts_pack");
     return YR_OK;
 }

@@ -87,6 +87,16 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// acc += x * w on four lanes with two packed FFMA2 (fma.rn.f32x2: each lane is an IEEE fused multiply-add, so the bits
+// equal four fmaf calls) - half the issue slots of scalar FFMAs in the issue-bound depthwise inner loops.
+__device__ __forceinline__ void fma4(float4& acc, const float4& x, const float4& w) {
+    unsigned long long* a = reinterpret_cast<unsigned long long*>(&acc);
+    const unsigned long long* xx = reinterpret_cast<const unsigned long long*>(&x);
+    const unsigned long long* ww = reinterpret_cast<const unsigned long long*>(&w);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a[0]) : "l"(xx[0]), "l"(ww[0]));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a[1]) : "l"(xx[1]), "l"(ww[1]));
+}
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 

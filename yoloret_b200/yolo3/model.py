@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from .._lib import YrLossParams
+from .._lib import YrLossParams, YrLoss3Params
 from ..engine import Engine
 from ..postprocess import PostProcess, ANCHOR_MASK
 from ..weights import load_checkpoint
@@ -301,3 +301,87 @@ def yolo_loss(y_trues: Sequence[torch.Tensor], yolo_outputs: Sequence[torch.Tens
     for idx, (yt, yo) in enumerate(zip(y_trues, yolo_outputs)):
         loss = loss + YoloLoss(idx, anchors, num_scales, ignore_thresh, box_loss, print_loss)(yt, yo)
     return loss
+
+
+# --------------------------------------------------------------------------------------
+class _FusedLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, loss_obj, y_true, *outs):
+        need = any(o.requires_grad for o in outs)
+        parts, dls = loss_obj._run(y_true, outs, need)
+        ctx.dls, ctx.n = dls, len(outs)
+        return parts[:, :3].sum()  # sum over scales of giou + confidence + class (train.py:11-16, model.py:669)
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.dls is None:
+            return (None, None) + (None,) * ctx.n
+        return (None, None) + tuple(d * g for d in ctx.dls)
+
+
+class FusedYoloLoss:
+    """The training loss of the reference - ``sum(YoloLoss(idx, ...)(y_true[idx], yolo_outputs[idx]))`` over the scales
+    (code/yolo3/model.py:585-671, code/yolo3/train.py:11-16) - in ONE kernel launch on a SPARSE y_true
+    (``utils.encode_true_boxes_sparse``): no dense y_true tensors, no per-scale launches, workspaces allocated once,
+    no host synchronisation, CUDA-graph capturable.  ``loss(y_true_sparse, [y1, y2, y3])`` returns the scalar total
+    wired into autograd; ``last_parts`` [3,4] holds (giou, confidence, class, sum(ignore_mask)) per scale."""
+
+    def __init__(self, anchors, num_scales=3, ignore_thresh=.5, box_loss=BOX_LOSS.GIOU):
+        if box_loss != BOX_LOSS.GIOU:
+            raise NameError("BOX_LOSS.MSE is dead code in the reference (undefined names); only GIOU is supported")
+        self.anchors = np.asarray(anchors, np.float32).reshape(-1, 2)
+        self.num_scales, self.ignore_thresh = int(num_scales), float(ignore_thresh)
+        self._key, self._ws, self._parts, self._dl, self._p = None, None, None, None, None
+        self.last_parts = None
+
+    def _prepare(self, y_true, outs):
+        key = (y_true.B, tuple(y_true.grids), y_true.num_classes, y_true.cap, tuple(tuple(o.shape) for o in outs),
+               outs[0].device)
+        if key == self._key:
+            return
+        p = YrLoss3Params()
+        E = 5 + y_true.num_classes
+        p.B, p.C, p.num_scales = y_true.B, y_true.num_classes, self.num_scales
+        mask = ANCHOR_MASK[-self.num_scales:]
+        steps = [32, 16, 8]
+        for l in range(self.num_scales):
+            gh, gw = y_true.grids[l]
+            if tuple(outs[l].shape) != (y_true.B, gh, gw, 3, E):
+                raise ValueError("yolo_outputs[%d] has shape %s, the sparse y_true expects %s"
+                                 % (l, tuple(outs[l].shape), (y_true.B, gh, gw, 3, E)))
+            p.gh[l], p.gw[l], p.ld_logits[l] = gh, gw, 3 * E
+            for k in range(3):
+                p.anchors[l][k][0] = float(self.anchors[mask[l][k]][0])
+                p.anchors[l][k][1] = float(self.anchors[mask[l][k]][1])
+        p.input_h, p.input_w = y_true.grids[0][0] * steps[0], y_true.grids[0][1] * steps[0]  # model.py:628
+        p.ignore_thresh, p.max_records = self.ignore_thresh, y_true.cap
+        dev = outs[0].device
+        nbytes = int(_lib.lib().yr_yolo_loss3_workspace(C.byref(p)))
+        if nbytes <= 0:
+            raise _lib.YrError("yr_yolo_loss3: unsupported configuration")
+        self._ws = torch.zeros((nbytes + 3) // 4, dtype=torch.int32, device=dev)   # zeroed once: holds the arrival counter
+        self._parts = torch.zeros(3, 4, dtype=torch.float32, device=dev)
+        self._dl = [torch.empty(tuple(o.shape), dtype=torch.float32, device=dev) for o in outs[:self.num_scales]]
+        self._p, self._key = p, key
+
+    def _run(self, y_true, outs, need_grad: bool):
+        if not all(o.is_cuda and o.dtype == torch.float32 for o in outs):
+            raise _lib.YrError("FusedYoloLoss needs float32 CUDA tensors (no CPU fallback exists)")
+        outs = [o.detach().contiguous() for o in outs[:self.num_scales]]
+        self._prepare(y_true, outs)
+        lib = _lib.lib()
+        dev = outs[0].device
+        with torch.cuda.device(dev):
+            lp = (C.c_void_p * 3)(*[o.data_ptr() for o in outs] + [None] * (3 - len(outs)))
+            mp = (C.c_void_p * 3)(*[m.data_ptr() for m in y_true.maps] + [None] * (3 - len(y_true.maps)))
+            dp = (C.c_void_p * 3)(*[d.data_ptr() for d in self._dl] + [None] * (3 - len(self._dl))) if need_grad else None
+            _lib.check(lib.yr_yolo_loss3(lp, mp, y_true.records.data_ptr(), y_true.counts.data_ptr(), C.byref(self._p),
+                                         self._parts.data_ptr(), dp, self._ws.data_ptr(), self._ws.numel() * 4,
+                                         torch.cuda.current_stream(dev).cuda_stream), "yr_yolo_loss3")
+        self.last_parts = self._parts
+        return self._parts, (self._dl if need_grad else None)
+
+    def __call__(self, y_true, yolo_outputs):
+        return _FusedLossFn.apply(self, y_true, *yolo_outputs[:self.num_scales])
+
+    call = __call__

@@ -116,3 +116,69 @@ def preprocess_true_boxes_gpu(true_boxes: torch.Tensor, input_shape, anchors, nu
     _lib.check(_lib.lib().yr_encode_true_boxes(tb.data_ptr(), B, T, anc.ctypes.data_as(C.POINTER(C.c_float)), h, w,
                                                num_classes, num_scales, ptrs, st), "yr_encode_true_boxes")
     return ys
+
+
+class SparseYTrue:
+    """Sparse y_true of a batch: what ``preprocess_true_boxes`` (reference
+    code/yolo3/utils.py:298-376) encodes, without the > 99.9 % zeros of the dense tensors.  Per scale ``l`` an int32 slot
+    map ``maps[l]`` [B,gh,gw,3] (record index or -1) and a record list ``records[l]`` [cap,8] = (x, y, w, h normalised
+    centre form, 4 words of class bits); ``counts`` [3] records per scale.  ``to_dense()`` rebuilds the reference's
+    tensors (the adapter for code that wants the reference signature)."""
+
+    def __init__(self, B, grids, num_classes, cap, device):
+        self.B, self.grids, self.num_classes, self.cap = int(B), [tuple(int(v) for v in g) for g in grids], int(num_classes), int(cap)
+        self.maps = [torch.full((self.B, g[0], g[1], 3), -1, dtype=torch.int32, device=device) for g in self.grids]
+        self.records = torch.zeros(3, self.cap, 8, dtype=torch.float32, device=device)
+        self.counts = torch.zeros(3, dtype=torch.int32, device=device)
+
+    def to_dense(self):
+        out = []
+        E = 5 + self.num_classes
+        counts = self.counts.cpu().numpy()
+        for l, (m, g) in enumerate(zip(self.maps, self.grids)):
+            y = torch.zeros(self.B, g[0], g[1], 3, E, dtype=torch.float32, device=m.device)
+            idx = torch.nonzero(m >= 0, as_tuple=False)
+            if len(idx):
+                if int(counts[l]) > self.cap:
+                    raise _lib.YrError("sparse y_true overflow: %d records > capacity %d" % (int(counts[l]), self.cap))
+                r = m[idx[:, 0], idx[:, 1], idx[:, 2], idx[:, 3]].long()
+                rec = self.records[l][r]
+                y[idx[:, 0], idx[:, 1], idx[:, 2], idx[:, 3], 0:4] = rec[:, 0:4]
+                y[idx[:, 0], idx[:, 1], idx[:, 2], idx[:, 3], 4] = 1.0
+                bits = rec[:, 4:8].contiguous().view(torch.int32)
+                for c in range(self.num_classes):
+                    on = ((bits[:, c >> 5] >> (c & 31)) & 1).float()
+                    y[idx[:, 0], idx[:, 1], idx[:, 2], idx[:, 3], 5 + c] = on
+            out.append(y)
+        return out
+
+
+def encode_true_boxes_sparse(true_boxes: torch.Tensor, input_shape, anchors, num_classes, num_scales=3,
+                             out: "SparseYTrue" = None) -> "SparseYTrue":
+    """``preprocess_true_boxes`` for a whole batch on the GPU, emitting the SPARSE form (slot maps + records) instead of
+    the dense tensors: same box -> (scale, cell, anchor) assignment, same slot-collision behaviour (reference
+    code/yolo3/utils.py:298-376).  ``true_boxes``: float32 CUDA [B,T,5] = (xmin, ymin, xmax, ymax, class) in input
+    pixels, zero-width rows are padding.  ``out``: a ``SparseYTrue`` to refill (no allocation; graph-capturable)."""
+    if not (true_boxes.is_cuda and true_boxes.dtype == torch.float32 and true_boxes.dim() == 3 and true_boxes.shape[2] == 5):
+        raise ValueError("encode_true_boxes_sparse expects a float32 CUDA tensor [B,T,5]")
+    if not (1 <= int(num_classes) <= 128):
+        raise ValueError("the sparse y_true holds up to 128 classes, got %d" % num_classes)
+    import ctypes as C
+    tb = true_boxes.contiguous()
+    B, T = int(tb.shape[0]), int(tb.shape[1])
+    h, w = int(input_shape[0]), int(input_shape[1])
+    anc = np.ascontiguousarray(np.asarray(anchors, np.float32).reshape(-1))
+    if anc.size != 18:
+        raise ValueError("preprocess_true_boxes needs the 9 anchors (18 numbers), got %d" % anc.size)
+    grids = [tuple(int(v) for v in np.round(np.array([h, w], np.int32) / s).astype(np.int32)) for s in (32, 16, 8)[:num_scales]]
+    if out is None:
+        out = SparseYTrue(B, grids, num_classes, max(1, B * T), tb.device)
+    elif out.B != B or out.grids != grids or out.num_classes != num_classes or out.cap < B * T:
+        raise ValueError("the SparseYTrue to refill does not match this batch")
+    with torch.cuda.device(tb.device):
+        ptrs = (C.c_void_p * 3)(*[m.data_ptr() for m in out.maps] + [None] * (3 - len(out.maps)))
+        st = torch.cuda.current_stream(tb.device).cuda_stream
+        _lib.check(_lib.lib().yr_encode_true_boxes_sparse(tb.data_ptr(), B, T, anc.ctypes.data_as(C.POINTER(C.c_float)), h, w,
+                                                          num_classes, num_scales, ptrs, out.records.data_ptr(),
+                                                          out.counts.data_ptr(), out.cap, st), "yr_encode_true_boxes_sparse")
+    return out
