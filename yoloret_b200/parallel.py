@@ -122,7 +122,7 @@ class GradBucket:
     all-reduce, code/train.py:55-56, and the loss SUM of code/yolo3/train.py:66-70).
 
     All gradients live in ONE flat fp32 bucket (2.63 M elements = 10.5 MB for MobileNetV2-0.75 COCO), padded
-    to a multiple of the world size.  ``reduce_scatter`` leaves each rank with the SUM of its 1/N shard
+    to a multiple of the world size (each shard a multiple of 32 elements).  ``reduce_scatter`` leaves each rank with the SUM of its 1/N shard
     (``ncclReduceScatter`` over NVLink; a sharded optimizer updates that shard), ``all_gather`` rebuilds the
     full vector (updated parameters).  The reference sums across replicas (it does not average, each
     replica divides by its LOCAL batch, code/yolo3/model.py:624-625) - so does this."""
@@ -131,7 +131,8 @@ class GradBucket:
         if numel <= 0 or world <= 0 or not (0 <= rank < world):
             raise ValueError("bad bucket: numel=%d world=%d rank=%d" % (numel, world, rank))
         self.numel, self.world, self.rank, self.group = numel, world, rank, group
-        self.shard_numel = (numel + world - 1) // world
+        # shards start on 128-byte boundaries (the optimizer kernel uses 128-bit accesses on a rank's shard)
+        self.shard_numel = ((numel + world - 1) // world + 31) // 32 * 32
         self.padded = self.shard_numel * world
         self.flat = torch.zeros(self.padded, dtype=torch.float32, device=device)
         self.shard = torch.zeros(self.shard_numel, dtype=torch.float32, device=device)
