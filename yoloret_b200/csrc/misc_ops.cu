@@ -1,6 +1,7 @@
 // Small streaming kernels of the YOLO-ReT graph: stem conv, nearest/max resampling,
 // the fused RFCR fusion and the squeeze-excite gate.  All are HBM/launch bound.
 #include "yr_common.cuh"
+#include <stdlib.h>
 
 namespace yr {
 
@@ -132,7 +133,7 @@ stem_kernel_v2(const void* __restrict__ in_, const float* __restrict__ wgt, cons
 constexpr int STEM_ROUNDS = 3;
 
 template <int ACT, bool U8, int CPT>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(320, 3)  // 3 CTAs per SM: the kernel is latency-bound at 2 (ncu: no pipe above 45 %)
 stem_kernel_v3(const void* __restrict__ in_, const float* __restrict__ wgt, const float* __restrict__ bias,
                float* __restrict__ out, int ld_out, int H, int W, int Ho, int Wo, int N, int pad_t, int pad_l, int TH,
                int row_floats) {
@@ -212,11 +213,13 @@ stem_kernel_v3(const void* __restrict__ in_, const float* __restrict__ wgt, cons
         const int ho = ho0 + r;
         if (ho >= Ho) break;
         const int n = cg * CPT;
-        float acc[4][CPT];
+        // channel PAIRS per packed FFMA2 (fma.rn.f32x2: each lane an IEEE fma, so the bits equal scalar fmaf): the
+        // kernel is FMA-issue bound (27 taps x CPT channels per pixel), the packed form halves its issue slots
+        float2 acc[4][CPT / 2];
 #pragma unroll
         for (int px = 0; px < 4; ++px)
 #pragma unroll
-            for (int j = 0; j < CPT; ++j) acc[px][j] = 0.0f;
+            for (int j = 0; j < CPT / 2; ++j) acc[px][j] = make_float2(0.0f, 0.0f);
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
             float x[28];
@@ -231,16 +234,17 @@ stem_kernel_v3(const void* __restrict__ in_, const float* __restrict__ wgt, cons
 #pragma unroll
                 for (int ci = 0; ci < 3; ++ci) {
                     const float* wp = sw + ((kh * 3 + kw) * 3 + ci) * N + n;
+                    float4 wv[CPT / 4];
 #pragma unroll
-                    for (int j4 = 0; j4 < CPT / 4; ++j4) {
-                        const float4 wv = *reinterpret_cast<const float4*>(wp + j4 * 4);
+                    for (int j4 = 0; j4 < CPT / 4; ++j4) wv[j4] = *reinterpret_cast<const float4*>(wp + j4 * 4);
 #pragma unroll
-                        for (int px = 0; px < 4; ++px) {
-                            const float xv = x[(2 * px + kw) * 3 + ci];
-                            acc[px][j4 * 4 + 0] = fmaf(xv, wv.x, acc[px][j4 * 4 + 0]);
-                            acc[px][j4 * 4 + 1] = fmaf(xv, wv.y, acc[px][j4 * 4 + 1]);
-                            acc[px][j4 * 4 + 2] = fmaf(xv, wv.z, acc[px][j4 * 4 + 2]);
-                            acc[px][j4 * 4 + 3] = fmaf(xv, wv.w, acc[px][j4 * 4 + 3]);
+                    for (int px = 0; px < 4; ++px) {
+                        const float xv = x[(2 * px + kw) * 3 + ci];
+                        const float2 xx = make_float2(xv, xv);
+#pragma unroll
+                        for (int j4 = 0; j4 < CPT / 4; ++j4) {
+                            fma2(acc[px][j4 * 2 + 0], xx, make_float2(wv[j4].x, wv[j4].y));
+                            fma2(acc[px][j4 * 2 + 1], xx, make_float2(wv[j4].z, wv[j4].w));
                         }
                     }
                 }
@@ -255,10 +259,10 @@ stem_kernel_v3(const void* __restrict__ in_, const float* __restrict__ wgt, cons
             for (int j4 = 0; j4 < CPT / 4; ++j4) {
                 const float4 bv = ldg4(bias + n + j4 * 4);
                 float4 v;
-                v.x = apply_act<ACT>(acc[px][j4 * 4 + 0] + bv.x);
-                v.y = apply_act<ACT>(acc[px][j4 * 4 + 1] + bv.y);
-                v.z = apply_act<ACT>(acc[px][j4 * 4 + 2] + bv.z);
-                v.w = apply_act<ACT>(acc[px][j4 * 4 + 3] + bv.w);
+                v.x = apply_act<ACT>(acc[px][j4 * 2 + 0].x + bv.x);
+                v.y = apply_act<ACT>(acc[px][j4 * 2 + 0].y + bv.y);
+                v.z = apply_act<ACT>(acc[px][j4 * 2 + 1].x + bv.z);
+                v.w = apply_act<ACT>(acc[px][j4 * 2 + 1].y + bv.w);
                 st4(o + j4 * 4, v);
             }
         }
@@ -270,8 +274,8 @@ template <int ACT, bool U8, int CPT>
 static bool launch_stem_v3(const yr_op& op, cudaStream_t s) {
     if (op.stride != 2 || op.W % 4 != 0 || op.B > 65535) return false;
     const int row_items = cdiv(op.Wo, 4) * (op.N / CPT);
-    if (row_items > 512) return false;
-    const int rows_per_round = 384 / row_items > 0 ? 384 / row_items : 1;
+    if (row_items > 320) return false;
+    const int rows_per_round = 320 / row_items > 0 ? 320 / row_items : 1;
     const int threads = (rows_per_round * row_items + 31) / 32 * 32;
     const int TH = rows_per_round * STEM_ROUNDS;
     // a thread reads 28 floats from float offset 24*g of its rows: the row needs 24*(groups-1) + 28 floats
@@ -308,7 +312,13 @@ static int launch_stem_act(const yr_op& op, cudaStream_t s) {
     const unsigned grid = (unsigned)((total + 255) / 256);
     const size_t smem = (size_t)27 * op.N * sizeof(float);
     // v3 with 4 channels per thread: the N/4 lanes of a pixel store one contiguous run (full 32-byte sectors)
-    if (op.in_is_u8 ? launch_stem_v3<ACT, true, 4>(op, s) : launch_stem_v3<ACT, false, 4>(op, s)) {
+    static const int cpt_knob = [] {  // experiment knob: channels per thread of the staged stem kernel (4 or 8)
+        const char* e = getenv("YR_STEM_CPT");
+        return e ? atoi(e) : 4;
+    }();
+    if (cpt_knob == 8 && op.N % 8 == 0 && (op.in_is_u8 ? launch_stem_v3<ACT, true, 8>(op, s) : launch_stem_v3<ACT, false, 8>(op, s))) {
+        // 8 channels per thread: each input value is packed once for four FFMA2
+    } else if (op.in_is_u8 ? launch_stem_v3<ACT, true, 4>(op, s) : launch_stem_v3<ACT, false, 4>(op, s)) {
     } else if (op.N % 12 == 0) {
         if (op.in_is_u8) launch_stem_v2<ACT, true, 12>(op, s);
         else launch_stem_v2<ACT, false, 12>(op, s);
@@ -470,7 +480,8 @@ rfcr_kernel(const float* __restrict__ b1, int ld1, int K1, const float* __restri
         float c1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // W1 . b1[h/2, w/2]: shared by both pixels
         {
             const float* x = b1 + (((size_t)b * H1 + (h >> 1)) * W1 + pp) * ld1;
-            for (int k = 0; k < K1; k += 4) {
+#pragma unroll 4
+            for (int k = 0; k < K1; k += 4) {  // unrolled: the loads of 4 steps are in flight together (latency-bound loop)
                 const float4 xv = ldg4(x + k);
                 const float* w = w1p + (size_t)k * N + n;
                 fma8(c1, xv.x, w); fma8(c1, xv.y, w + N); fma8(c1, xv.z, w + 2 * N); fma8(c1, xv.w, w + 3 * N);
@@ -483,6 +494,7 @@ rfcr_kernel(const float* __restrict__ b1, int ld1, int K1, const float* __restri
             for (int i = 0; i < 8; ++i) c2[j][i] = c4[j][i] = 0.f;
         {
             const float* x = b2 + (((size_t)b * H + h) * W + p0) * ld2;
+#pragma unroll 2
             for (int k = 0; k < K2; k += 4) {
                 const float4 xa = ldg4(x + k), xb = ldg4(x + ld2 + k);
                 const float* w = w2p + (size_t)k * N + n;
@@ -499,6 +511,7 @@ rfcr_kernel(const float* __restrict__ b1, int ld1, int K1, const float* __restri
                 for (int i = 0; i < 8; ++i) d[q][i] = 0.f;
             const float* x = b3 + (((size_t)b * 2 * H + 2 * h) * (2 * W) + 2 * (p0 + j)) * ld3;
             const size_t rs = (size_t)2 * W * ld3;
+#pragma unroll 2
             for (int k = 0; k < K3; k += 4) {
                 const float4 x0 = ldg4(x + k), x1 = ldg4(x + ld3 + k), x2 = ldg4(x + rs + k), x3 = ldg4(x + rs + ld3 + k);
                 const float* w = w3p + (size_t)k * N + n;
@@ -625,12 +638,30 @@ int launch_se(const yr_op& op, cudaStream_t s) {
 // (dwconv.cu): the global mean never re-reads the activation.  One CTA per image.
 //   w = [w1t R x F | w2 R x F],  bias = [b1 R | b2 F]   (w1 TRANSPOSED so a warp reads it coalesced)
 // ---------------------------------------------------------------------------------
-// One CTA serves SE_IPC images, so every weight row fetched from L2 feeds SE_IPC dot products (a CTA per image had
-// 256 CTAs pulling the same 0.5 MB of weights through the same L2 slices at the same time: 58 us for F = 512).
-// Per image the arithmetic and its order are those of a CTA-per-image kernel: lane-strided partial sums + xor-shuffle
-// tree for the first FC, a sequential fmaf chain over r for the second, so the gate of an image does not depend on its
-// position in the batch.
+// A CLUSTER of SE_CS CTAs serves SE_IPC images: every weight row fetched from L2 feeds SE_IPC dot products, and the
+// two FC layers - whose loops are pure L2 latency - are cut SE_CS ways so the chains are short: CTA `rank` computes
+// hidden units [rank * R/CS, ...) one row per warp, writes them into EVERY CTA's shared memory through distributed
+// shared memory (st.shared::cluster), and after one cluster barrier computes gate channels [rank * F/CS, ...), eight
+// threads per channel over disjoint r ranges combined by a fixed xor-shuffle tree.  (The round-1 kernel - one CTA per
+// 4 images, 16 CTAs at batch 64 - took 33 us for F = 512: 8 sequential rows per warp, then 128 sequential loads per
+// thread.)  Per image the arithmetic and its order do not depend on the batch position or the cluster rank layout.
 constexpr int SE_IPC = 4;
+constexpr int SE_CS = 8;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f32(const float* local_smem, uint32_t cta, float v) {
+    uint32_t la = (uint32_t)__cvta_generic_to_shared(local_smem), ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(cta));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 __global__ void __launch_bounds__(512)
 se_fc_kernel(const float* __restrict__ part, int slots, int HW, int F, int R, int B, const float* __restrict__ w1t,
@@ -640,16 +671,18 @@ se_fc_kernel(const float* __restrict__ part, int slots, int HW, int F, int R, in
     pdl_wait();
     pdl_launch_dependents();
     float* mean = sm;                 // [SE_IPC][F]
-    float* hid = sm + SE_IPC * F;     // [SE_IPC][R]
+    float* hid = sm + SE_IPC * F;     // [SE_IPC][R]  (filled by all CTAs of the cluster)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const int img0 = blockIdx.x * SE_IPC;
+    const int rank = (int)cluster_ctarank();
+    const int img0 = (blockIdx.x / SE_CS) * SE_IPC;
     const int F4 = F >> 2;
     for (int i = tid; i < SE_IPC * F4; i += blockDim.x) {
         const int im = i / F4, f4 = i - im * F4;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         if (img0 + im < B) {
             const float* pb = part + (size_t)(img0 + im) * slots * F;
-            for (int sl = 0; sl < slots; ++sl) {  // fixed order: deterministic
+#pragma unroll 8   // independent loads in flight; the adds keep their fixed order (deterministic)
+            for (int sl = 0; sl < slots; ++sl) {
                 const float4 v = ldg4(pb + (size_t)sl * F + f4 * 4);
                 a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
             }
@@ -658,11 +691,13 @@ se_fc_kernel(const float* __restrict__ part, int slots, int HW, int F, int R, in
         st4(mean + im * F + f4 * 4, make_float4(a.x / d, a.y / d, a.z / d, a.w / d));
     }
     __syncthreads();
-    for (int r = warp; r < R; r += nwarps) {
+    // ---- first FC + swish: this CTA's slice of the hidden units, broadcast to the whole cluster ----
+    const int RPC = (R + SE_CS - 1) / SE_CS;
+    for (int r = rank * RPC + warp; r < min(R, (rank + 1) * RPC); r += nwarps) {
         float a[SE_IPC];
 #pragma unroll
         for (int im = 0; im < SE_IPC; ++im) a[im] = 0.f;
-#pragma unroll 8   // 8 independent weight loads in flight per lane: the loop is L2-latency bound otherwise
+#pragma unroll 8   // 8 independent weight loads in flight per lane
         for (int f = lane; f < F; f += 32) {
             const float w = __ldg(w1t + (size_t)r * F + f);
 #pragma unroll
@@ -673,31 +708,47 @@ se_fc_kernel(const float* __restrict__ part, int slots, int HW, int F, int R, in
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) a[im] += __shfl_xor_sync(0xffffffffu, a[im], o);
         }
-        if (lane == 0) {
-            const float bb = __ldg(b1 + r);
+        const float bb = __ldg(b1 + r);
+        if (lane < SE_CS) {  // lane c delivers the row's SE_IPC values to CTA c
 #pragma unroll
             for (int im = 0; im < SE_IPC; ++im) {
                 const float v = a[im] + bb;
-                hid[im * R + r] = v * (1.0f / (1.0f + expf(-v)));
+                st_cluster_f32(hid + im * R + r, (uint32_t)lane, v * (1.0f / (1.0f + expf(-v))));
             }
         }
     }
-    __syncthreads();
-    for (int f = tid; f < F; f += blockDim.x) {
+    cluster_sync_all();
+    // ---- second FC + sigmoid: this CTA's slice of the gate channels, 8 threads per channel ----
+    const int FPC = (F + SE_CS - 1) / SE_CS;
+    const int sub = tid & 7;
+    const int r_lo = (R * sub) / 8, r_hi = (R * (sub + 1)) / 8;
+    for (int fo = tid >> 3; fo < FPC; fo += blockDim.x >> 3) {
+        const int f = rank * FPC + fo;
+        const bool ok = f < F;
         float a[SE_IPC];
 #pragma unroll
         for (int im = 0; im < SE_IPC; ++im) a[im] = 0.f;
+        if (ok) {
 #pragma unroll 8
-        for (int r = 0; r < R; ++r) {
-            const float w = __ldg(w2 + (size_t)r * F + f);
+            for (int r = r_lo; r < r_hi; ++r) {
+                const float w = __ldg(w2 + (size_t)r * F + f);
 #pragma unroll
-            for (int im = 0; im < SE_IPC; ++im) a[im] = fmaf(hid[im * R + r], w, a[im]);
+                for (int im = 0; im < SE_IPC; ++im) a[im] = fmaf(hid[im * R + r], w, a[im]);
+            }
         }
-        const float bb = __ldg(b2 + f);
 #pragma unroll
-        for (int im = 0; im < SE_IPC; ++im)
-            if (img0 + im < B) gate[(size_t)(img0 + im) * F + f] = 1.0f / (1.0f + expf(-(a[im] + bb)));
+        for (int im = 0; im < SE_IPC; ++im) {
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) a[im] += __shfl_xor_sync(0xffffffffu, a[im], o);
+        }
+        if (ok && sub == 0) {
+            const float bb = __ldg(b2 + f);
+#pragma unroll
+            for (int im = 0; im < SE_IPC; ++im)
+                if (img0 + im < B) gate[(size_t)(img0 + im) * F + f] = 1.0f / (1.0f + expf(-(a[im] + bb)));
+        }
     }
+    // no CTA may exit while another can still write into its shared memory: all writes happened before the barrier above
 }
 
 int launch_se_fc(const yr_op& op, cudaStream_t s) {
@@ -706,9 +757,25 @@ int launch_se_fc(const yr_op& op, cudaStream_t s) {
     YR_CHECK_ARG(F % 4 == 0 && R > 0 && slots > 0 && op.H > 0 && op.W > 0, "se_fc: unsupported F=%d R=%d slots=%d", F, R, slots);
     const size_t smem = (size_t)SE_IPC * (F + R) * sizeof(float);
     YR_CHECK_ARG(smem <= 48 * 1024, "se_fc: F too large");
-    launch_pdl(se_fc_kernel, dim3(cdiv(op.B, SE_IPC)), dim3(512), smem, s, (const float*)op.in, slots, op.H * op.W, F, R, op.B,
-               op.w, op.bias, op.w + (size_t)F * R, op.bias + R, (float*)op.out);
-    YR_CHECK_LAUNCH("se_fc");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cdiv(op.B, SE_IPC) * SE_CS);
+    cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = SE_CS;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    if (cudaLaunchKernelEx(&cfg, se_fc_kernel, (const float*)op.in, slots, op.H * op.W, F, R, op.B, op.w, op.bias,
+                           op.w + (size_t)F * R, op.bias + R, (float*)op.out) != cudaSuccess) {
+        set_error("se_fc: cluster launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return YR_ERR_CUDA;
+    }
     return YR_OK;
 }
 

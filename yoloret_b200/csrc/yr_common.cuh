@@ -97,6 +97,13 @@ __device__ __forceinline__ void fma4(float4& acc, const float4& x, const float4&
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a[1]) : "l"(xx[1]), "l"(ww[1]));
 }
 
+// acc += a * b on two lanes with one packed FFMA2 (each lane an IEEE fma)
+__device__ __forceinline__ void fma2(float2& acc, const float2& a, const float2& b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;"
+        : "+l"(*reinterpret_cast<unsigned long long*>(&acc))
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+}
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
