@@ -75,8 +75,12 @@ struct Params {
     uint32_t a_slot_bytes, b_slot_bytes;  // ring slot sizes (depthwise front: halo'd box / weight slot + dw taps)
     // depthwise front: spatial tiling of the output (an item = one TH x TW tile of one image)
     int TH, TW, IW, tiles_h, tiles_w, Ho, Wo, pad_t, pad_l, dw_act;
+    int conv_groups;  // converter groups taking k-blocks round-robin: 2, or 3 in the stride-1 depthwise front (the second
+                      // epilogue group's warps convert instead: narrow outputs leave the epilogue idle, the depthwise
+                      // phase is what bounds those layers); ring sizes are multiples of it
     int epi_groups;  // 2 (the groups alternate tiles) or 1 (stride-2 depthwise front: shared memory goes to the boxes)
     long long* dbg;
+    int dbg_skip;  // debug instantiation only (YR_DWPW_SKIP): 1 = no depthwise math, 2 = no TMA box loads, 4 = no staging/phase 2 math
 };
 constexpr int DW_TAIL_BYTES = 2048;  // per weight slot: 9 x 32 depthwise taps + 32 biases (1280 B), padded to 2 KB
 
@@ -343,9 +347,12 @@ __device__ __forceinline__ void dw_converter_loop(const Params& p, const uint8_t
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)p.a_col0;
     const uint32_t dw_off = 2u * p.BN * 128u;
     const uint32_t bar_id = 3u + (uint32_t)grp;
+    int turn = 0;  // dq % conv_groups
     for (int item = item0; item < item1; ++item) {
         for (int kb = 0; kb < p.KB; ++kb, ++dq) {
-            if ((int)(dq & 1u) == grp) {
+            const bool mine = turn == grp;
+            if (++turn == p.conv_groups) turn = 0;
+            if (mine) {
                 uint32_t bslot;
                 if (p.resident) {
                     bslot = (uint32_t)kb;
@@ -367,7 +374,7 @@ __device__ __forceinline__ void dw_converter_loop(const Params& p, const uint8_t
                 for (int t = 0; t < PH; ++t)
 #pragma unroll
                     for (int o = 0; o < PW; ++o) acc[t][o] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (worker) {
+                if (worker && !(DBG && (p.dbg_skip & 1))) {
 #pragma unroll
                 for (int rr = 0; rr < IN_ROWS; ++rr) {
                     float4 x[IN_COLS];
@@ -467,7 +474,7 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
     const uint32_t b_off = a_off + p.nA * p.a_slot_bytes;
     const uint32_t epi_off = b_off + p.nB * b_slot_bytes;
     const uint32_t stage_off = epi_off + (uint32_t)(p.epi_groups * p.epi_group_bytes);  // depthwise front: 2 staging tiles
-    const uint32_t bar_off = stage_off + (FRONT != 0 ? 2u * (uint32_t)A_TILE_BYTES : 0u);
+    const uint32_t bar_off = stage_off + (FRONT != 0 ? (uint32_t)p.conv_groups * (uint32_t)A_TILE_BYTES : 0u);
     const uint32_t bar0 = base + bar_off;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gbase + bar_off + 8u * BAR_COUNT);
 
@@ -532,6 +539,12 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
                 }
                 for (int kb = 0; kb < p.KB; ++kb) {
                     mbar_wait(bar0 + 8u * (BAR_A_EMPTY + ra.slot), ra.phase ^ 1u, 1);
+                    if (DBG && FRONT != 0 && (p.dbg_skip & 2)) {
+                        mbar_expect_tx(bar0 + 8u * (BAR_A_FULL + ra.slot), 0);
+                        dbg_mark(p, 0, dq++);
+                        ra.advance(p.nA);
+                        continue;
+                    }
                     mbar_expect_tx(bar0 + 8u * (BAR_A_FULL + ra.slot), box_bytes);
                     if constexpr (FRONT != 0)
                         tma_load_4d(base + a_off + ra.slot * p.a_slot_bytes, &tmA, bar0 + 8u * (BAR_A_FULL + ra.slot), kb * BK,
@@ -635,6 +648,13 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
         // ===== epilogue =====
         const int ew8 = warp - (2 + NUM_CONVERTERS / 32);
         const int ew = ew8 & 3, eg = ew8 >> 2;
+        if constexpr (FRONT != 0) {
+            if (eg == 1 && p.conv_groups == 3) {  // third converter group (see Params::conv_groups)
+                dw_converter_loop<FRONT ? FRONT : 1, DBG>(p, gbase + a_off, gbase + b_off,
+                                                           reinterpret_cast<float*>(gbase + stage_off + 2 * A_TILE_BYTES), tmem_base,
+                                                           bar0, item0, item1, warp & 3, lane, 2);
+            }
+        }
         float* stg = reinterpret_cast<float*>(gbase + epi_off + eg * p.epi_group_bytes) + ew * 32 * EPI_LD;
         float* s_bias = reinterpret_cast<float*>(gbase + epi_off + eg * p.epi_group_bytes + EPI_STAGE_BYTES);
         if (eg < p.epi_groups) {  // (a single-group launch leaves the second group's warps idle: it has no buffers)
@@ -733,7 +753,7 @@ struct Tiling {
     int BN, n_tiles, KB, nA, nT, nB, nAcc, resident, acc_stride, a_col0, epi_group_bytes;
     size_t smem;
     // depthwise front
-    int TH, TW, IH, IW, tiles_h, tiles_w, epi_groups;
+    int TH, TW, IH, IW, tiles_h, tiles_w, epi_groups, conv_groups;
     uint32_t a_slot, b_slot;
 };
 
@@ -804,44 +824,53 @@ static bool make_tiling_dw(int K, int N, int S, int Ho, int Wo, Tiling& t) {
     static const int shapes[9][2] = {{8, 16}, {16, 8}, {4, 32}, {32, 4}, {2, 64}, {4, 16}, {8, 8}, {16, 4}, {2, 32}};
     long long best = -1;
     Tiling bt = t;
+    static const int groups_knob = [] {  // experiment knob: 3 turns the second epilogue group into a third converter
+        const char* e = getenv("YR_DWPW_GROUPS");  // group (stride 1).  Measured on B200: no gain (104x104x144 -> 24: 205 us
+        return e ? atoi(e) : 2;                    // either way; 208x208x24 -> 16: 238 vs 201 us), so the default is 2.
+    }();
     for (int i = 0; i < 9; ++i) {
-        Tiling c = t;
-        const int TH = shapes[i][0], TW = shapes[i][1];
-        c.TH = TH; c.TW = TW;
-        c.IW = (TW - 1) * S + 3; c.IH = (TH - 1) * S + 3;
-        if (c.IW > 256 || c.IH > 256 || (long long)c.IW * c.IH * 128 > DW_BOX_LIMIT) continue;
-        c.a_slot = (uint32_t)(((long long)c.IW * c.IH * 128 + 1023) / 1024 * 1024);
-        c.b_slot = 2u * c.BN * 128u + DW_TAIL_BYTES;
-        // stride 2: the boxes are ~4x the tile, so one epilogue group gives its transpose buffers up
-        c.epi_groups = c.a_slot > 40 * 1024 ? 1 : 2;
-        const long long fixed = 1024 + (long long)c.epi_groups * c.epi_group_bytes + 2ll * A_TILE_BYTES + BAR_BYTES;  // + 2 staging tiles
-        const long long avail = SMEM_LIMIT - fixed;
-        if (c.KB <= MAX_B && (long long)c.KB * c.b_slot + 2ll * c.a_slot <= avail) {
-            c.resident = 1;
-            c.nB = c.KB;
-        } else {
-            // streamed weights: EVEN ring (a slot then always belongs to the same converter group, which sees every one
-            // of its mbarrier phases - the converters read the depthwise taps from the slot), after two boxes for the A ring
-            c.resident = 0;
-            long long nb = (avail - 2ll * c.a_slot) / c.b_slot;
-            if (c.a_slot <= 32 * 1024 && (avail - 4ll * c.a_slot) / c.b_slot >= 4) nb = (avail - 4ll * c.a_slot) / c.b_slot;
-            if (nb > 6) nb = 6;
-            nb &= ~1ll;
-            if (nb < 2) continue;
-            c.nB = (int)nb;
-        }
-        long long na = (avail - (long long)c.nB * c.b_slot) / c.a_slot;
-        if (na > 6) na = 6;
-        na &= ~1ll;  // even: see make_tiling
-        if (na < 2) continue;
-        c.nA = (int)na;
-        c.smem = (size_t)(fixed + (long long)c.nA * c.a_slot + (long long)c.nB * c.b_slot);
-        if (c.smem > (size_t)SMEM_LIMIT) continue;
-        const long long tiles = (long long)((Ho + TH - 1) / TH) * ((Wo + TW - 1) / TW);
-        const long long cost = tiles * ((long long)c.IW * c.IH + 96);
-        if (best < 0 || cost < best) {
-            best = cost;
-            bt = c;
+        for (int G = (S == 1 && groups_knob >= 3) ? 3 : 2; G >= 2; --G) {
+            Tiling c = t;
+            const int TH = shapes[i][0], TW = shapes[i][1];
+            c.TH = TH; c.TW = TW;
+            c.IW = (TW - 1) * S + 3; c.IH = (TH - 1) * S + 3;
+            if (c.IW > 256 || c.IH > 256 || (long long)c.IW * c.IH * 128 > DW_BOX_LIMIT) continue;
+            c.a_slot = (uint32_t)(((long long)c.IW * c.IH * 128 + 1023) / 1024 * 1024);
+            c.b_slot = 2u * c.BN * 128u + DW_TAIL_BYTES;
+            c.conv_groups = G;
+            // three converter groups borrow the second epilogue group's warps; stride 2: the boxes are ~4x the tile, so
+            // one epilogue group gives its transpose buffers up
+            c.epi_groups = (G == 3 || c.a_slot > 40 * 1024) ? 1 : 2;
+            if (c.nT < G) continue;
+            c.nT = c.nT / G * G;  // every ring is a multiple of the group count: a slot always belongs to one group,
+                                  // which then sees every mbarrier phase of it (see make_tiling on even rings)
+            const long long fixed = 1024 + (long long)c.epi_groups * c.epi_group_bytes + (long long)G * A_TILE_BYTES + BAR_BYTES;
+            const long long avail = SMEM_LIMIT - fixed;
+            if (c.KB <= MAX_B && (long long)c.KB * c.b_slot + (long long)G * c.a_slot <= avail) {
+                c.resident = 1;
+                c.nB = c.KB;
+            } else {
+                c.resident = 0;
+                long long nb = (avail - (long long)G * c.a_slot) / c.b_slot;
+                if (c.a_slot <= 32 * 1024 && (avail - 2ll * G * c.a_slot) / c.b_slot >= 2 * G) nb = (avail - 2ll * G * c.a_slot) / c.b_slot;
+                if (nb > 6) nb = 6;
+                nb = nb / G * G;
+                if (nb < G) continue;
+                c.nB = (int)nb;
+            }
+            long long na = (avail - (long long)c.nB * c.b_slot) / c.a_slot;
+            if (na > 6) na = 6;
+            na = na / G * G;
+            if (na < G) continue;
+            c.nA = (int)na;
+            c.smem = (size_t)(fixed + (long long)c.nA * c.a_slot + (long long)c.nB * c.b_slot);
+            if (c.smem > (size_t)SMEM_LIMIT) continue;
+            const long long tiles = (long long)((Ho + TH - 1) / TH) * ((Wo + TW - 1) / TW);
+            const long long cost = tiles * ((long long)c.IW * c.IH + 96) * (G == 3 ? 2 : 3);  // 3 groups: ~1.5x the front rate
+            if (best < 0 || cost < best) {
+                best = cost;
+                bt = c;
+            }
         }
     }
     if (best < 0) return false;
@@ -925,6 +954,7 @@ int launch_dwpw(const yr_op& op, cudaStream_t s) {
     p.TH = t.TH; p.TW = t.TW; p.IW = t.IW; p.tiles_h = t.tiles_h; p.tiles_w = t.tiles_w;
     p.Ho = op.Ho; p.Wo = op.Wo; p.pad_t = op.pad_t; p.pad_l = op.pad_l; p.dw_act = op.mode;
     p.epi_groups = t.epi_groups;
+    p.conv_groups = t.conv_groups;
     static DeviceOnce attr_once;  // function attributes are per device
     bool& attr_set = attr_once.cur();
     if (!attr_set) {
@@ -942,12 +972,15 @@ int launch_dwpw(const yr_op& op, cudaStream_t s) {
     const int grid = (p.total_items + p.items_per_cta - 1) / p.items_per_cta;
     p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(t.BN >> 3) << 17) | ((uint32_t)(ts::BM >> 4) << 24);
     p.dbg = nullptr;
+    p.dbg_skip = 0;
     static const bool debug = getenv("YR_PW_TC_DEBUG") != nullptr;  // developer aid only: timeline of CTA 0
     if (debug) {
         static long long* dbuf = nullptr;
         if (!dbuf) cudaMalloc(&dbuf, 8 * ts::DBG_EV * sizeof(long long));
         cudaMemsetAsync(dbuf, 0, 8 * ts::DBG_EV * sizeof(long long), s);
         p.dbg = dbuf;
+        const char* e = getenv("YR_DWPW_SKIP");
+        p.dbg_skip = e ? atoi(e) : 0;
     }
     auto kern = op.stride == 1 ? (debug ? ts::pw_ts_kernel<true, 1> : ts::pw_ts_kernel<false, 1>)
                                : (debug ? ts::pw_ts_kernel<true, 2> : ts::pw_ts_kernel<false, 2>);
@@ -962,8 +995,8 @@ int launch_dwpw(const yr_op& op, cudaStream_t s) {
         const char* names[8] = {"tma_issue", "a_full_seen", "t_empty_seen", "conv_done", "mma_start", "mma_issued",
                                 "acc_full_seen", "epi_done"};
         long long t0 = h[0];
-        fprintf(stderr, "dwpw timeline C=%d N=%d s%d %dx%d tile %dx%d box %dx%d tiles %dx%d BN=%d KB=%d nA=%d nT=%d nB=%d nAcc=%d resident=%d items/cta=%d grid=%d smem=%zu\n",
-                p.K, p.N, op.stride, op.Ho, op.Wo, t.TH, t.TW, t.IH, t.IW, t.tiles_h, t.tiles_w, p.BN, p.KB, p.nA, p.nT, p.nB,
+        fprintf(stderr, "dwpw timeline groups=%d C=%d N=%d s%d %dx%d tile %dx%d box %dx%d tiles %dx%d BN=%d KB=%d nA=%d nT=%d nB=%d nAcc=%d resident=%d items/cta=%d grid=%d smem=%zu\n",
+                p.conv_groups, p.K, p.N, op.stride, op.Ho, op.Wo, t.TH, t.TW, t.IH, t.IW, t.tiles_h, t.tiles_w, p.BN, p.KB, p.nA, p.nT, p.nB,
                 p.nAcc, p.resident, p.items_per_cta, grid, t.smem);
         for (int r = 0; r < 8; ++r) {
             fprintf(stderr, "%-14s", names[r]);
@@ -1043,6 +1076,7 @@ int launch_pw_ts(const yr_op& op, cudaStream_t s) {
     p.TH = p.TW = p.IW = p.tiles_h = p.tiles_w = 1;
     p.Ho = p.Wo = p.pad_t = p.pad_l = p.dw_act = 0;
     p.epi_groups = 2;
+    p.conv_groups = 2;
     static DeviceOnce attr_once;  // function attributes are per device
     bool& attr_set = attr_once.cur();
     if (!attr_set) {
@@ -1063,6 +1097,7 @@ int launch_pw_ts(const yr_op& op, cudaStream_t s) {
     const int grid = (p.total_items + p.items_per_cta - 1) / p.items_per_cta;
     p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(t.BN >> 3) << 17) | ((uint32_t)(ts::BM >> 4) << 24);
     p.dbg = nullptr;
+    p.dbg_skip = 0;
     static const bool debug = getenv("YR_PW_TC_DEBUG") != nullptr;  // developer aid only: timeline of CTA 0
     if (debug) {
         static long long* dbuf = nullptr;
