@@ -98,6 +98,32 @@ def test_fused_depthwise_pointwise_equals_separate(built_lib, anchors, name, hw,
     assert mf.engine.build_plan(0, B)[1] == mu.engine.build_plan(0, B)[1] - len(mf.engine.dwpw_blob)
 
 
+@pytest.mark.parametrize("name,hw,B", [("mobilenetv2x75", (128, 160), 3), ("efficientnetb3", (64, 96), 2),
+                                       ("efficientnetlite0", (96, 128), 2)])
+def test_folded_linear_convs_match_unfolded(built_lib, anchors, name, hw, B):
+    """NetDef.fold_linear_pairs (a linear 1x1 conv + BN folded into the 1x1 convs that are its only readers: the stage
+    project conv into the y conv / the next 1x1, reference code/yolo3/model.py:91-115,283-318) computes the same function:
+    logits of the folded engine (default) vs the layer-by-layer engine within 3e-4 x max, both within the usual tolerance
+    of the oracle, with fewer layers and fewer algorithmic bytes."""
+    ncls = 80
+    nd = NetDef(name, ncls, hw)
+    w = synthetic_weights(nd.weight_shapes, ncls, seed=43)
+    x = torch.rand(B, hw[0], hw[1], 3, generator=torch.Generator().manual_seed(8))
+    mf = yolov3_body((B, hw[0], hw[1], 3), name, 3, num_classes=ncls, fold_linear=True).set_weights(w, anchors)
+    mu = yolov3_body((B, hw[0], hw[1], 3), name, 3, num_classes=ncls, fold_linear=False).set_weights(w, anchors)
+    assert len(mf.engine.folded) >= 4 and len(mu.engine.folded) == 0
+    assert len(mf.engine.net.layers) == len(mu.engine.net.layers) - len(mf.engine.folded)
+    assert mf.engine.net.totals()["bytes"] < mu.engine.net.totals()["bytes"]
+    yf, yu = mf(x.cuda()), mu(x.cuda())
+    ref = [y.numpy() for y in ograph.forward(w, x, name, ncls)]
+    for a, b, r in zip(yf, yu, ref):
+        a, b = a.cpu().numpy(), b.cpu().numpy()
+        scale = max(1.0, float(np.abs(r).max()))
+        assert float(np.abs(a - b).max()) <= 3e-4 * scale   # two fp32 evaluation orders of the same function
+        _logits_close(a, r, 0, "folded")
+        _logits_close(b, r, 0, "unfolded")
+
+
 def test_fused_upsampling_equals_separate_resample(built_lib, anchors):
     """The engine folds UpSampling2D into the producing 1x1 conv's epilogue (block_20_conv / block_24_conv): logits
     bit-identical to running the resample op on its own, with fewer launches."""
@@ -200,6 +226,34 @@ def test_detect_image_golden(built_lib, tmp_path, variant):
         assert np.abs(fb - ref_fb).max(initial=0) <= 1e-2
     img = yolo.detect_image(g["jpeg_0"].tobytes(), draw=True)
     assert img.size == (500, 375)
+
+
+def test_detect_images_batch_equals_single_image_calls(built_lib, tmp_path):
+    """``YOLO.detect_images`` (host decode, per-image GPU letterbox into the batch, one network pass, per-image un-mapping)
+    on the 7 demo JPEGs of different sizes == the committed goldens == seven separate ``detect_image`` calls."""
+    g = np.load(os.path.join(GOLD, "demo_golden.npz"))
+    (tmp_path / "anchors.txt").write_text(",  ".join("%g,%g" % (a, b) for a, b in g["anchors"]))
+    classes = ["aeroplane", "bicycle", "bird", "boat", "bottle", "bus", "car", "cat", "chair", "cow", "diningtable",
+               "dog", "horse", "motorbike", "person", "pottedplant", "sheep", "sofa", "train", "tvmonitor"]
+    (tmp_path / "classes.txt").write_text("\n".join(classes) + "\n")
+    flags = {"backbone": BACKBONE.MOBILENETV2x75, "classes_path": str(tmp_path / "classes.txt"),
+             "anchors_path": str(tmp_path / "anchors.txt"), "input_size": (320, 320), "score": 0.3, "nms": 0.5,
+             "weights": _golden_weights(), "model": "golden", "quiet": True}
+    n = len(g["names"])
+    many = YOLO(dict(flags, batch=8))
+    one = YOLO(dict(flags, batch=1))
+    jpegs = [g["jpeg_%d" % i].tobytes() for i in range(n)]
+    got = many.detect_images([io.BytesIO(j) if i % 2 else j for i, j in enumerate(jpegs)])
+    assert len(got) == n
+    for i in range(n):
+        boxes, scores, cls = got[i]
+        assert np.array_equal(cls, g["det_classes_%d" % i])
+        np.testing.assert_allclose(scores, g["det_scores_%d" % i], atol=TOL)
+        assert np.abs(boxes.astype(np.int64) - g["det_boxes_i_%d" % i]).max(initial=0) <= 1
+        sb, ss, sc = one.detect_image(jpegs[i], draw=False)
+        assert np.array_equal(sc, cls) and np.array_equal(sb, boxes) and np.array_equal(ss, scores)
+    with pytest.raises(ValueError):
+        many.detect_images([])
 
 
 def test_calculate_map_on_demo_images(built_lib, tmp_path):

@@ -668,6 +668,9 @@ se_fc_kernel(const float* __restrict__ part, int slots, int HW, int F, int R, in
              const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
              float* __restrict__ gate) {
     extern __shared__ __align__(16) float sm[];
+    // Distributed shared memory may only be written once the target CTA has started executing: arrive now, wait right
+    // before the first remote store (compute-sanitizer racecheck flags the stores otherwise).
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     pdl_wait();
     pdl_launch_dependents();
     float* mean = sm;                 // [SE_IPC][F]
@@ -691,6 +694,7 @@ se_fc_kernel(const float* __restrict__ part, int slots, int HW, int F, int R, in
         st4(mean + im * F + f4 * 4, make_float4(a.x / d, a.y / d, a.z / d, a.w / d));
     }
     __syncthreads();
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // every CTA of the cluster is running
     // ---- first FC + swish: this CTA's slice of the hidden units, broadcast to the whole cluster ----
     const int RPC = (R + SE_CS - 1) / SE_CS;
     for (int r = rank * RPC + warp; r < min(R, (rank + 1) * RPC); r += nwarps) {

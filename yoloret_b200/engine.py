@@ -62,7 +62,7 @@ class Engine:
                  num_scales: int = 3, max_boxes: int = 20, cand_cap: Optional[int] = None,
                  device: Optional[torch.device] = None, pw_variant: int = _lib.PW_AUTO, input_u8: bool = False,
                  fuse_se: bool = True, fuse_mbconv: bool = False, lanes: int = 1, autotune: bool = True, fuse_up2: bool = True,
-                 num_anchors: int = 3, fuse_dwpw: bool = True):
+                 num_anchors: int = 3, fuse_dwpw: bool = True, fold_linear: bool = True):
         if not torch.cuda.is_available():
             raise _lib.YrError("yoloret_b200.Engine needs a CUDA device (no CPU fallback exists)")
         self.lib = _lib.lib()
@@ -73,16 +73,20 @@ class Engine:
             self.device = torch.device("cuda", torch.cuda.current_device())
         with torch.cuda.device(self.device):  # allocations, attribute caches and the autotuner run on that GPU
             self._init(model_name, num_classes, input_hw, batch, weights, anchors, micro_batch, num_scales, max_boxes,
-                       cand_cap, pw_variant, input_u8, fuse_se, fuse_mbconv, lanes, autotune, fuse_up2, num_anchors, fuse_dwpw)
+                       cand_cap, pw_variant, input_u8, fuse_se, fuse_mbconv, lanes, autotune, fuse_up2, num_anchors, fuse_dwpw,
+                       fold_linear)
 
     def _init(self, model_name, num_classes, input_hw, batch, weights, anchors, micro_batch, num_scales, max_boxes,
-              cand_cap, pw_variant, input_u8, fuse_se, fuse_mbconv, lanes, autotune, fuse_up2, num_anchors, fuse_dwpw=True):
+              cand_cap, pw_variant, input_u8, fuse_se, fuse_mbconv, lanes, autotune, fuse_up2, num_anchors, fuse_dwpw=True, fold_linear=True):
         # the reference derives anchors per scale as num_anchors // num_scales (code/yolo.py:214-216); decode, the head
         # width and the y_true layout of this engine are written for 3 per scale (every shipped anchor file: 9 / 3)
         if int(num_anchors) != 3:
             raise ValueError("this engine supports 3 anchors per scale (got %d): pass 9 anchors with num_scales=3"
                              % int(num_anchors))
         self.net = NetDef(model_name, num_classes, input_hw, int(num_anchors))
+        # linear 1x1 convs whose only readers are 1x1 convs are folded into them (NetDef.fold_linear_pairs): the
+        # 255-channel head tensors between a stage's project conv and its y / next conv never touch HBM
+        self.folded = self.net.fold_linear_pairs() if fold_linear else []
         self.model_name, self.num_classes, self.input_hw = model_name, num_classes, tuple(input_hw)
         self.batch = int(batch)
         # lanes > 1: the micro-batches of a step run concurrently on that many CUDA streams (fork/join inside the
@@ -170,7 +174,14 @@ class Engine:
             if L.kind == "pw":
                 k = w[L.conv + "/kernel"][0, 0].astype(np.float64)          # [Cin, Cout]
                 s, b = _fold_bn(w, L.bn, k.shape[1])
-                mat = _pad_cols(_expand_rows(k * s[None, :], L.inp[0].segs), L.out.C)
+                k = k * s[None, :]
+                A = L.extra.get("fold_from")
+                if A is not None:  # B(A(x)) = x (W_A W_B) + (b_A W_B + b_B), in float64 (NetDef.fold_linear_pairs)
+                    ka = w[A.conv + "/kernel"][0, 0].astype(np.float64)
+                    sa, ba = _fold_bn(w, A.bn, ka.shape[1])
+                    b = ba @ k + b
+                    k = (ka * sa[None, :]) @ k
+                mat = _pad_cols(_expand_rows(k, L.inp[0].segs), L.out.C)
                 self.wdev[i] = (self._dev(mat), self._dev(_pad_cols(b, L.out.C)))
                 if self.pw_variant in (_lib.PW_AUTO, _lib.PW_TC):
                     self.wtc[i] = self._pack_tc(self.wdev[i][0], _lib.PW_TC)

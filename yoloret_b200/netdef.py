@@ -416,6 +416,56 @@ class NetDef:
             if v.buf is dead:
                 self.taps[k] = View(new.buf, new.off + v.off, v.segs)
 
+    # ---- graph-level folding ---------------------------------------------------------
+    def fold_linear_pairs(self) -> List[str]:
+        """Folds a LINEAR 1x1 conv (+BN, no activation, no residual) into the 1x1 convs that are its only readers.
+
+        Every head stage ends in such a conv - the MBConv project conv + BN, `x` of
+        make_last_layers_efficientnet_lite (reference code/yolo3/model.py:91-115) - and in the bottom-up half of
+        yolov3_body that `x` is read by 1x1 convs only: the `y` conv (model.py:110-114) and the next 1x1 + BN + ReLU6
+        (model.py:296-305, 309-318), or the first conv of the next stage (c3, model.py:283-295).  With A: t = x W_A + b_A
+        and B: act(t W_B + b_B), B(A(x)) = act(x (W_A W_B) + (b_A W_B + b_B)): the 255-channel tensor t - at 52x52 the
+        widest tensor of the head - is never written or read, and the flops drop too (128 -> 255 -> {255, 128} becomes
+        128 -> {255, 128}).  Same function in exact arithmetic; like the BatchNorm folding it is done once on the
+        host in float64.  The folded conv inherits A's input view and SE gate.  Returns the names of the folded layers."""
+        done: List[str] = []
+        changed = True
+        while changed:
+            changed = False
+            for A in list(self.layers):
+                if A.kind != "pw" or A.act != "none" or A.res is not None or "fold_from" in A.extra:
+                    continue
+                buf = A.out.buf
+                if buf.full_batch or A.out.off != 0 or buf.ld != A.out.C:
+                    continue
+                if sum(1 for L in self.layers if L.out.buf is buf) != 1:
+                    continue
+                cons = [L for L in self.layers if any(v.buf is buf for v in L.inp) or (L.res is not None and L.res.buf is buf)]
+                if not cons or not all(L.kind == "pw" and L.gate is None and len(L.inp) == 1 and L.inp[0].buf is buf
+                                       and L.inp[0].off == 0 and L.inp[0].C == A.out.C and L.res is None
+                                       and "fold_from" not in L.extra for L in cons):
+                    continue
+                ka, na = A.inp[0].Clog, A.out.Clog
+                before = (ka + na) + sum(na + L.out.Clog for L in cons)
+                after = sum(ka + L.out.Clog for L in cons)
+                if after >= before:
+                    continue
+                x = A.inp[0]
+                for L in cons:
+                    L.extra["fold_from"] = A
+                    L.inp = [x]
+                    L.gate = A.gate
+                    L.name = "%s*%s" % (A.name, L.name)
+                    cout = L.out.Clog
+                    L.flops = 2 * x.H * x.W * x.Clog * cout
+                    L.bytes_alg = x.H * x.W * (x.Clog + cout) * 4 + (x.Clog * cout + 2 * cout) * 4
+                self.layers.remove(A)
+                self.bufs.remove(buf)
+                done.append(A.name)
+                changed = True
+                break
+        return done
+
     # ---- accounting (SURVEY.md §8d) ------------------------------------------------
     def totals(self) -> Dict[str, float]:
         t: Dict[str, float] = {"flops": 0, "bytes": 0}

@@ -104,7 +104,7 @@ class YOLO(object):
         def model_body(inputs, **kw):
             return yolov3_body(inputs, model_name=backbone_name, drop_rate=0.2, data_format="channels_last", **kw)
 
-        extra = {k: FLAGS[k] for k in ('micro_batch', 'device', 'pw_variant', 'fuse_se', 'fuse_mbconv', 'lanes', 'autotune', 'fuse_up2', 'fuse_dwpw') if k in FLAGS}
+        extra = {k: FLAGS[k] for k in ('micro_batch', 'device', 'pw_variant', 'fuse_se', 'fuse_mbconv', 'lanes', 'autotune', 'fuse_up2', 'fuse_dwpw', 'fold_linear') if k in FLAGS}
         self.yolo_model = YoloModel(model_body, num_anchors, self.num_scales, self.class_names, model_path,
                                     self.anchors, self.input_shape, self.score, self.nms, self.with_classes,
                                     batch=batch, weights=weights, input_u8=bool(FLAGS.get('input_u8', False)),
@@ -178,6 +178,33 @@ class YOLO(object):
         if unpack:
             return e.results()
         return e.pp.padded_views(e.pp.read_wire())
+
+    def detect_images(self, images):
+        """Batched ``detect_image`` (the reference handles one image per call, code/yolo.py:235): ``images`` is a list of
+        up to ``batch`` encoded images (bytes or binary file objects) of ANY sizes.  Each is decoded on the host (PIL, as
+        ``parse_image`` does, code/yolo.py:105-112), letterboxed on the GPU straight into its row of the engine's input
+        batch (``letterbox_image``, code/yolo3/utils.py:67-83) and mapped back to its own image shape by ``yolo_eval``;
+        ONE network pass serves the whole list.  Returns per image what ``detect_image(image, draw=False)`` returns."""
+        from PIL import Image
+        e = self.engine
+        if not (1 <= len(images) <= e.batch):
+            raise ValueError("detect_images takes 1..%d images (the engine's batch), got %d" % (e.batch, len(images)))
+        dst = e.input_slot(0, False)
+        shapes = np.tile(np.asarray(self.input_shape, np.float32), (e.batch, 1))
+        for b, im in enumerate(images):
+            data = im if isinstance(im, bytes) else im.read()
+            arr = np.array(Image.open(io.BytesIO(data)).convert("RGB"), dtype=np.uint8)
+            shapes[b] = arr.shape[:2]
+            letterbox_image(torch.from_numpy(arr).to(e.device, non_blocking=True), self.input_shape, out=dst[b])
+        if len(images) < e.batch:
+            dst[len(images):].zero_()
+        e.pp.set_image_shapes(shapes)
+        if getattr(self, "_batch_graphs", None) is None:
+            self._batch_graphs = {}
+        if False not in self._batch_graphs:
+            self._batch_graphs[False] = e.capture(self.score, self.nms, 0, False)
+        self._batch_graphs[False].replay()
+        return e.results()[:len(images)]
 
     def detect_stream(self, batches, image_shapes=None, unpack: bool = True, gather=None, gather_read: bool = True):
         """Pipelined ``detect_batch`` over an iterable of host batches (pinned memory recommended; uint8 or float32):

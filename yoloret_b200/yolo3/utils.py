@@ -30,19 +30,23 @@ def letterbox_geometry(ih: int, iw: int, size):
     return nh, nw, (h - nh) // 2, (w - nw) // 2
 
 
-def letterbox_image(image: torch.Tensor, size) -> torch.Tensor:
+def letterbox_image(image: torch.Tensor, size, out: torch.Tensor = None) -> torch.Tensor:
     """reference code/yolo3/utils.py:67-83 on the GPU.
 
     ``image``: uint8 CUDA tensor [ih, iw, 3] (a decoded image).  Returns float32
     [h, w, 3] in [0,1]: (1/255) scaling as tf.io.decode_image(dtype=float32), bilinear
-    half-pixel resize keeping aspect ratio, zero padding."""
+    half-pixel resize keeping aspect ratio, zero padding.  ``out``: a contiguous float32 CUDA
+    [h, w, 3] tensor to write into (e.g. one image of an engine's input batch) instead of a new one."""
     if not (image.is_cuda and image.dtype == torch.uint8 and image.dim() == 3 and image.shape[2] == 3):
         raise ValueError("letterbox_image expects a uint8 CUDA tensor [H,W,3]")
     image = image.contiguous()
     ih, iw = int(image.shape[0]), int(image.shape[1])
     h, w = int(size[0]), int(size[1])
     nh, nw, dy, dx = letterbox_geometry(ih, iw, size)
-    out = torch.empty(h, w, 3, dtype=torch.float32, device=image.device)
+    if out is None:
+        out = torch.empty(h, w, 3, dtype=torch.float32, device=image.device)
+    elif not (out.is_cuda and out.dtype == torch.float32 and tuple(out.shape) == (h, w, 3) and out.is_contiguous()):
+        raise ValueError("letterbox_image: out must be a contiguous float32 CUDA tensor [%d,%d,3]" % (h, w))
     st = torch.cuda.current_stream(image.device).cuda_stream
     _lib.check(_lib.lib().yr_letterbox_u8(image.data_ptr(), ih, iw, out.data_ptr(), h, w, nh, nw, dy, dx, st),
                "yr_letterbox_u8")
