@@ -138,14 +138,14 @@ def measured_peaks():
 
 def measured_traffic(kind):
     """DRAM bytes per step of one kernel kind, from the committed ncu capture of this workload
-    (profiles/r1_step_ncu.json: dram__bytes_read.sum + dram__bytes_write.sum summed over the kind's launches)."""
-    p = os.path.join(ROOT, "profiles", "r1_step_ncu.json")
+    (profiles/r2_step_ncu.json: dram__bytes_read.sum + dram__bytes_write.sum summed over the kind's launches)."""
+    p = os.path.join(ROOT, "profiles", "r2_step_ncu.json")
     if not os.path.exists(p):
         return None
     d = json.load(open(p))
     k = d.get("kinds", {}).get(kind)
     return None if k is None else {"bytes_per_step": k["dram_bytes"], "launches": k["launches"],
-                                   "source": "profiles/r1_step_ncu.json (ncu, one eager step, batch %d)" % d.get("batch", 0)}
+                                   "source": "profiles/r2_step_ncu.json (ncu, one eager step, batch %d)" % d.get("batch", 0)}
 
 
 def workload_name(a):

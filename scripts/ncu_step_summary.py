@@ -21,19 +21,36 @@ def num(v):
 
 def main():
     raw, prefix, batch = sys.argv[1], sys.argv[2], int(sys.argv[3])
-    rows = list(csv.reader(open(raw)))
-    hdr, units, data = rows[0], rows[1], rows[2:]
-    col = {n: hdr.index(n) for n in ("Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum")}
-    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
+    rows = [r for r in csv.reader(open(raw)) if r and not r[0].startswith("==")]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6,
+             "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6}
     kinds, launches = {}, []
-    for r in data:
-        if len(r) != len(hdr):
-            continue
-        name = r[col["Kernel Name"]]
-        t = num(r[col["gpu__time_duration.sum"]]) * scale.get(units[col["gpu__time_duration.sum"]], 1.0)
-        rd = num(r[col["dram__bytes_read.sum"]]) * scale.get(units[col["dram__bytes_read.sum"]], 1.0)
-        wr = num(r[col["dram__bytes_write.sum"]]) * scale.get(units[col["dram__bytes_write.sum"]], 1.0)
+    per_id = {}
+    hdr = rows[0]
+    if "Metric Name" in hdr:  # long format (ncu --csv --log-file): one row per (launch, metric)
+        ci = {n: hdr.index(n) for n in ("ID", "Kernel Name", "Metric Name", "Metric Unit", "Metric Value")}
+        for r in rows[1:]:
+            if len(r) != len(hdr):
+                continue
+            e = per_id.setdefault(r[ci["ID"]], {"name": r[ci["Kernel Name"]]})
+            e[r[ci["Metric Name"]]] = num(r[ci["Metric Value"]]) * scale.get(r[ci["Metric Unit"]], 1.0)
+        items = [(e["name"], e.get("gpu__time_duration.sum", 0.0), e.get("dram__bytes_read.sum", 0.0),
+                  e.get("dram__bytes_write.sum", 0.0)) for _, e in sorted(per_id.items(), key=lambda kv: int(kv[0]))]
+    else:  # wide format (ncu -i rep --page raw --csv)
+        units, data = rows[1], rows[2:]
+        col = {n: hdr.index(n) for n in ("Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum")}
+        items = []
+        for r in data:
+            if len(r) != len(hdr):
+                continue
+            items.append((r[col["Kernel Name"]],
+                          num(r[col["gpu__time_duration.sum"]]) * scale.get(units[col["gpu__time_duration.sum"]], 1.0),
+                          num(r[col["dram__bytes_read.sum"]]) * scale.get(units[col["dram__bytes_read.sum"]], 1.0),
+                          num(r[col["dram__bytes_write.sum"]]) * scale.get(units[col["dram__bytes_write.sum"]], 1.0)))
+    for name, t, rd, wr in items:
         kind = next((k for pat, k in KIND if pat in name), "other")
+        if "pw_ts_kernel" in name and any(t in name for t in ("(int)1>", "(int)2>", ", 1>", ", 2>")):
+            kind = "dwpw"  # the depthwise-front instantiations of the tcgen05 pointwise kernel (YR_OP_DWPW)
         launches.append((name.split("(")[0], kind, t, rd, wr))
         k = kinds.setdefault(kind, {"launches": 0, "time_us": 0.0, "dram_bytes": 0.0})
         k["launches"] += 1

@@ -120,8 +120,7 @@ def test_folded_linear_convs_match_unfolded(built_lib, anchors, name, hw, B):
         a, b = a.cpu().numpy(), b.cpu().numpy()
         scale = max(1.0, float(np.abs(r).max()))
         assert float(np.abs(a - b).max()) <= 3e-4 * scale   # two fp32 evaluation orders of the same function
-        _logits_close(a, r, 0, "folded")
-        _logits_close(b, r, 0, "unfolded")
+        _logits_close(a, r, 0, "folded")   # (the layer-by-layer engine vs the oracle is test_network_matches_oracle)
 
 
 def test_fused_upsampling_equals_separate_resample(built_lib, anchors):
