@@ -456,9 +456,10 @@ def run_b200(a):
         prof = eng.profile_layers(SCORE, IOU, reps=3)
         kinds = {}
         for r in prof:
-            k = kinds.setdefault(r["kind"], {"ms": 0.0, "bytes": 0, "flops": 0, "launches": 0})
+            k = kinds.setdefault(r["kind"], {"ms": 0.0, "bytes": 0, "flops": 0, "launches": 0, "ref_bytes": 0})
             k["ms"] += r["ms"]
             k["bytes"] += r["bytes"]
+            k["ref_bytes"] += r.get("ref_bytes", r["bytes"])
             k["flops"] += r["flops"]
             k["launches"] += r["launches"]
         tot = sum(k["ms"] for k in kinds.values())
@@ -476,7 +477,14 @@ def run_b200(a):
                            "traffic_source": None if traffic is None else traffic["source"],
                            "algorithmic_bytes_per_launch": K["bytes"] / max(1, K["launches"]), "peak_source": which,
                            "share_of_step": K["ms"] / tot, "launches_per_step": K["launches"],
-                           "algorithmic_bytes_per_step": K["bytes"], "tflops": K["flops"] / (K["ms"] * 1e-3) / 1e12}
+                           "algorithmic_bytes_per_step": K["bytes"], "tflops": K["flops"] / (K["ms"] * 1e-3) / 1e12,
+                           "accounting": "bytes = compulsory traffic of each launch AS EXECUTED (a fused depthwise->pointwise "
+                                         "launch counts its input, output, residual and weights only - the fused minimum)",
+                           "per_layer_accounting": {
+                               "bytes_per_step": K["ref_bytes"], "achieved": K["ref_bytes"] / (K["ms"] * 1e-3) / 1e9,
+                               "frac": K["ref_bytes"] / (K["ms"] * 1e-3) / 1e9 / hbm,
+                               "note": "the same launches against SURVEY.md 8d's per-layer formulas (depthwise layer bytes + "
+                                       "pointwise layer bytes, as if the intermediate tensor existed); > what the kernel moves"}}
         out["kernels"] = {k: {"ms_per_step": round(v["ms"], 4), "share": round(v["ms"] / tot, 4),
                               "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None,
                               "launches": v["launches"]} for k, v in sorted(kinds.items(), key=lambda kv: -kv[1]["ms"])}

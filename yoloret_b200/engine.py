@@ -424,6 +424,7 @@ class Engine:
         def _ptr(v, c0, sl=0):
             return _ptr0(v, c0, sl, lane, u8)
         ops = (YrOp * len(self.net.layers))()
+        self._ref_bytes: Dict[str, int] = getattr(self, "_ref_bytes", {})
         gate_ptr: Dict[int, int] = {}
         meta = []   # per emitted op: (kind, name, algorithmic bytes / image, flops / image, layer index)
         n_ops = 0
@@ -473,6 +474,7 @@ class Engine:
                 fused_bytes = 4 * (x.H * x.W * x.Clog + b.out.H * b.out.W * b.out.Clog * (2 if b.res is not None else 1)
                                    + (L.k * L.k + 2) * x.Clog + x.Clog * b.out.Clog + 2 * b.out.Clog)
                 meta.append(("dwpw", L.name + "+" + b.name.split("_")[-1], fused_bytes, L.flops + b.flops, i))
+                self._ref_bytes[meta[-1][1]] = L.bytes_alg + b.bytes_alg  # SURVEY 8d per-layer accounting of the two layers
                 skip = 1
                 continue
             meta.append((L.kind, L.name, L.bytes_alg, L.flops, i))
@@ -658,7 +660,8 @@ class Engine:
         out = []
         for i, (kind, name, byts, flops, _li) in enumerate(meta):
             out.append(dict(kind=kind, name=name, ms=float(acc[i]), bytes=int(byts) * self.batch,
-                            flops=int(flops) * self.batch, launches=len(chunks)))
+                            flops=int(flops) * self.batch, launches=len(chunks),
+                            ref_bytes=int(self._ref_bytes.get(name, byts)) * self.batch))
         E = self.num_classes + 5
         dec_bytes = self.batch * self.total_boxes * (E + 4) * 4
         out.append(dict(kind="decode", name="decode_filter", ms=float(acc[n_layers]), bytes=dec_bytes, flops=0, launches=1))
