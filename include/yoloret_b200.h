@@ -48,7 +48,7 @@ typedef enum yr_op_kind {
     YR_OP_RFCR = 4,      /* fused RFCR fusion: 4x 1x1 conv + resize + weighted sum */
     YR_OP_SE = 5,        /* squeeze-excite gate: global mean -> FC -> swish -> FC -> sigmoid */
     YR_OP_SE_FC = 6,     /* the same gate from the channel sums a DW op left in `aux` (fused squeeze) */
-    YR_OP_MBCONV = 7,    /* fused inverted-residual block: 1x1 expand + 3x3 depthwise + 1x1 project (+ residual) */
+    /* 7: retired (the round-1 expand+depthwise+project kernel, superseded by DWPW) */
     YR_OP_DWPW = 8       /* fused 3x3 depthwise (+BN +act) -> 1x1 conv (+BN +act +residual): the depthwise output never
                             exists in HBM */
 } yr_op_kind;
@@ -90,11 +90,6 @@ typedef enum yr_resample_mode { YR_UP2 = 0, YR_POOL2 = 1, YR_POOL4 = 2 } yr_resa
  *  SE_FC    in = the aux buffer of the producing DW op [B][K2 slots][C=F]; H,W = spatial size of the
  *           squeezed tensor; w = [w1^T R x F | w2 R x F] (first FC TRANSPOSED), bias = b1[R] then b2[F];
  *           N = R; out = gate [B][F].
- *  MBCONV   in [B,H,W,ld_in] C=Cin (<= 32); K2 = expanded channels Ce (<= 160); N = Cout (<= 32);
- *           k=3, stride 1|2, pad_t/pad_l = leading TF-SAME pads of the depthwise; ReLU6 after expand and
- *           depthwise, linear project; res optional [B,Ho,Wo,ld_res] (stride 1); w_tc = yr_mbconv_pack image
- *           of the three layers' folded weights; out [B,Ho,Wo,ld_out].  One kernel for block_N_expand ..
- *           block_N_add of tf.keras.applications.MobileNetV2 (reference code/yolo3/override.py:339-341).
  *  DWPW     in [B,H,W,ld_in] C channels (multiple of 8); k=3, stride 1|2, pad_t/pad_l = leading TF-SAME pads;
  *           mode = yr_act of the depthwise conv; N = output channels of the 1x1 conv (<= 192), act = its activation;
  *           bias = the 1x1 conv's bias [N]; res optional [B,Ho,Wo,ld_res]; w_tc = yr_dwpw_pack image (both layers'
@@ -153,14 +148,6 @@ int yr_pw_tc_pack(const float* w, int K, int N, float* packed, void* stream);
 /* Same for the variant-3 kernel (its n tiles are at most 192 columns wide, so the image differs). */
 int64_t yr_pw_ts_packed_floats(int K, int N);
 int yr_pw_ts_pack(const float* w, int K, int N, float* packed, void* stream);
-
-/* Fused inverted-residual block (YR_OP_MBCONV): packs the folded weights of its three layers -
- *   w1 [Cin][ld1] + b1[Ce] (expand), wd [9][ldd] + b2[Ce] (depthwise), w2 [Ce][ld2] + b3[Cout] (project) -
- * into the shared-memory image the kernel bulk-copies.  yr_mbconv_packed_floats returns 0 when the block
- * does not fit the fused kernel (the caller then runs the three ops separately). */
-int64_t yr_mbconv_packed_floats(int Cin, int Ce, int Cout);
-int yr_mbconv_pack(const float* w1, int ld1, const float* b1, const float* wd, int ldd, const float* b2,
-                   const float* w2, int ld2, const float* b3, int Cin, int Ce, int Cout, float* packed, void* stream);
 
 /* Fused depthwise -> pointwise pair (YR_OP_DWPW): w_pw [K][N] (the PW op's `w`), w_dw [9][K] + b_dw [K] (the DW op's
  * `w` / `bias`; K = the depthwise channel count = the 1x1 conv's input channels).  yr_dwpw_packed_floats returns 0

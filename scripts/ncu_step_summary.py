@@ -8,8 +8,7 @@ import sys
 
 KIND = [("decode", "decode"), ("pw_tc_kernel", "pw"), ("pw_ts_kernel", "pw"), ("pw_simt_kernel", "pw"), ("dw_tma_kernel", "dw"), ("dw_kernel", "dw"),
         ("se_fc_kernel", "se"), ("se_kernel", "se"), ("stem_kernel", "stem"), ("rfcr_kernel", "rfcr"),
-        ("resample_kernel", "resample"), ("nms_kernel", "nms"), ("pack_kernel", "pack"),
-        ("mbconv_kernel", "mbconv")]
+        ("resample_kernel", "resample"), ("nms_kernel", "nms"), ("pack_kernel", "pack")]
 
 
 def num(v):

@@ -63,21 +63,6 @@ def test_network_matches_oracle(built_lib, anchors, name, ncls, hw, B, micro, va
         assert float(t[..., 3 * (ncls + 5):].abs().max().item() if t.shape[-1] > 3 * (ncls + 5) else 0.0) == 0.0
 
 
-def test_fused_blocks_equal_unfused(built_lib, anchors):
-    """Engine with the fused inverted-residual kernel (blocks 1..5) == engine running every layer separately."""
-    hw, ncls, B = (128, 160), 80, 3
-    nd = NetDef("mobilenetv2x75", ncls, hw)
-    w = synthetic_weights(nd.weight_shapes, ncls, seed=21)
-    x = torch.rand(B, hw[0], hw[1], 3, generator=torch.Generator().manual_seed(5)).cuda()
-    mf = yolov3_body((B, hw[0], hw[1], 3), "mobilenetv2x75", 3, num_classes=ncls, fuse_mbconv=True).set_weights(w, anchors)
-    mu = yolov3_body((B, hw[0], hw[1], 3), "mobilenetv2x75", 3, num_classes=ncls, fuse_mbconv=False).set_weights(w, anchors)
-    assert len(mf.engine.mb_blob) >= 4 and len(mu.engine.mb_blob) == 0
-    yf = [y.clone() for y in mf(x)]
-    yu = [y.clone() for y in mu(x)]
-    for a, b in zip(yf, yu):
-        assert torch.equal(a, b), float((a - b).abs().max())
-
-
 @pytest.mark.parametrize("name,hw,B", [("mobilenetv2x75", (128, 160), 3), ("mobilenetv2x14", (96, 96), 2),
                                        ("efficientnetlite0", (96, 128), 2), ("efficientnetb3", (64, 96), 2)])
 def test_fused_depthwise_pointwise_equals_separate(built_lib, anchors, name, hw, B):

@@ -405,62 +405,6 @@ def test_fused_squeeze_excite(built_lib, B, H, W, F_, R, k, s):
     assert torch.equal(gates[0], gates[1])
 
 
-@pytest.mark.parametrize("B,H,W,Cin,Ce,Cout,stride,use_res", [
-    (2, 16, 32, 24, 144, 24, 1, True),     # exactly 2x2 tiles of 8x16
-    (3, 21, 19, 24, 144, 24, 1, True),     # ragged tiles on both axes
-    (2, 26, 38, 16, 96, 24, 2, False),     # stride 2, even input: TF SAME pads (0,1)
-    (2, 13, 13, 24, 144, 24, 2, False),    # stride 2, odd input: pads (1,1)
-    (1, 9, 7, 8, 40, 16, 1, False),        # small channels: one partial chunk, CoutP = 16
-    (5, 40, 48, 24, 144, 24, 1, True),     # > 148 tiles: several tiles per CTA, both D buffers
-])
-def test_fused_mbconv(built_lib, B, H, W, Cin, Ce, Cout, stride, use_res):
-    """YR_OP_MBCONV (expand+ReLU6 -> depthwise3x3+ReLU6 -> project [+res]) vs an fp64 reference and, bit for bit,
-    vs the same three layers run as separate ops (pw_tc, dw, pw_tc)."""
-    x = _rand(B, H, W, Cin, seed=1)
-    w1, b1 = _rand(Cin, Ce, seed=2, scale=Cin ** -0.5), _rand(Ce, seed=3, scale=0.3)
-    wd, b2 = _rand(9, Ce, seed=4, scale=0.4), _rand(Ce, seed=5, scale=0.3)
-    w2, b3 = _rand(Ce, Cout, seed=6, scale=Ce ** -0.5), _rand(Cout, seed=7, scale=0.3)
-    e = torch.clamp(x.double() @ w1.double() + b1.double(), 0, 6)
-    dref, (Ho, Wo, pt, pl) = _dw_ref(e, wd.double(), b2.double(), 3, stride, "relu6")
-    ref = dref @ w2.double() + b3.double()
-    if use_res:
-        ref = ref + x.double()
-    lib = built_lib
-    n = int(lib.yr_mbconv_packed_floats(Cin, Ce, Cout))
-    assert n > 0
-    dev = [t.cuda() for t in (x, w1, b1, wd, b2, w2, b3)]
-    xd, w1d, b1d, wdd, b2d, w2d, b3d = dev
-    blob = torch.full((n,), float("nan"), device="cuda")
-    st = torch.cuda.current_stream().cuda_stream
-    _lib.check(lib.yr_mbconv_pack(w1d.data_ptr(), Ce, b1d.data_ptr(), wdd.data_ptr(), Ce, b2d.data_ptr(), w2d.data_ptr(),
-                                  Cout, b3d.data_ptr(), Cin, Ce, Cout, blob.data_ptr(), st), "yr_mbconv_pack")
-    torch.cuda.synchronize()
-    assert not torch.isnan(blob).any()
-    out = torch.full((B, Ho, Wo, Cout + 8), float("nan"), device="cuda")
-    op = YrOp()
-    op.kind = _lib.OP_MBCONV
-    op.B, op.H, op.W, op.C, op.K2, op.Ho, op.Wo, op.N = B, H, W, Cin, Ce, Ho, Wo, Cout
-    op.k, op.stride, op.pad_t, op.pad_l, op.ld_in, op.ld_out = 3, stride, pt, pl, Cin, Cout + 8
-    op.in_, op.out, op.w_tc = xd.data_ptr(), out.data_ptr(), blob.data_ptr()
-    if use_res:
-        op.res, op.ld_res = xd.data_ptr(), Cin
-    run_op(op)
-    got = out[..., :Cout].cpu()
-    assert torch.isnan(out[..., Cout:]).all(), "kernel wrote outside its channel slice"
-    torch.testing.assert_close(got.double(), ref, rtol=5e-5, atol=5e-5)
-    # the unfused chain through the same ABI
-    ed = pw_op(xd, w1d, b1d, "relu6", variant=2)
-    dd = torch.empty(B, Ho, Wo, Ce, device="cuda")
-    dop = YrOp()
-    dop.kind, dop.act = _lib.OP_DW, ACT["relu6"]
-    dop.B, dop.H, dop.W, dop.C, dop.Ho, dop.Wo, dop.N = B, H, W, Ce, Ho, Wo, Ce
-    dop.k, dop.stride, dop.pad_t, dop.pad_l, dop.ld_in, dop.ld_out = 3, stride, pt, pl, Ce, Ce
-    dop.in_, dop.out, dop.w, dop.bias = ed.data_ptr(), dd.data_ptr(), wdd.data_ptr(), b2d.data_ptr()
-    run_op(dop)
-    un = pw_op(dd, w2d, b3d, "none", res=xd if use_res else None, variant=2)
-    assert torch.equal(un.cpu(), got), "fused block differs from the unfused chain: max %g" % float((un.cpu() - got).abs().max())
-
-
 def test_bad_arguments_fail_loudly(built_lib):
     op = YrOp()
     op.kind = _lib.OP_PW

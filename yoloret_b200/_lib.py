@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libyoloret_b200.so")
 
 # enums (include/yoloret_b200.h)
 ACT_NONE, ACT_RELU6, ACT_SWISH = 0, 1, 2
-OP_STEM, OP_PW, OP_DW, OP_RESAMPLE, OP_RFCR, OP_SE, OP_SE_FC, OP_MBCONV, OP_DWPW = 0, 1, 2, 3, 4, 5, 6, 7, 8
+OP_STEM, OP_PW, OP_DW, OP_RESAMPLE, OP_RFCR, OP_SE, OP_SE_FC, OP_DWPW = 0, 1, 2, 3, 4, 5, 6, 8
 UP2, POOL2, POOL4 = 0, 1, 2
 PW_AUTO, PW_SIMT, PW_TC, PW_TS = 0, 1, 2, 3
 
@@ -79,8 +79,6 @@ SYMBOLS = {
     "yr_pw_tc_pack": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "yr_pw_ts_packed_floats": (C.c_int64, [C.c_int, C.c_int]),
     "yr_pw_ts_pack": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
-    "yr_mbconv_packed_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
-    "yr_mbconv_pack": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "yr_dwpw_packed_floats": (C.c_int64, [C.c_int, C.c_int]),
     "yr_dwpw_pack": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "yr_dwpw_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),

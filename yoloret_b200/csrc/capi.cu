@@ -94,7 +94,6 @@ extern "C" int yr_run_ops(const yr_op* ops, int n_ops, void* stream) {
             case YR_OP_RFCR: rc = launch_rfcr(op, s); break;
             case YR_OP_SE: rc = launch_se(op, s); break;
             case YR_OP_SE_FC: rc = launch_se_fc(op, s); break;
-            case YR_OP_MBCONV: rc = launch_mbconv(op, s); break;
             case YR_OP_DWPW: rc = launch_dwpw(op, s); break;
             default:
                 set_error("run_ops: op %d has unknown kind %d", i, op.kind);

@@ -775,7 +775,12 @@ static bool make_tiling(int K, int N, Tiling& t) {
     const long long fixed = 1024 + 2ll * t.epi_group_bytes + BAR_BYTES;
     const long long avail = SMEM_LIMIT - fixed;
     const long long wbytes = (long long)t.n_tiles * t.KB * slot;
-    if (t.n_tiles * t.KB <= MAX_B && wbytes + 4 * tile <= avail) {
+    static const int res_na = [] {  // experiment knob: raw A tiles that must still fit beside a RESIDENT weight image
+        const char* e = getenv("YR_PW_RESIDENT_NA");
+        const int r = e ? atoi(e) : 4;
+        return r >= 2 && r <= 8 ? (r & ~1) : 4;
+    }();
+    if (t.n_tiles * t.KB <= MAX_B && wbytes + res_na * tile <= avail) {
         t.resident = 1;
         t.nB = t.n_tiles * t.KB;
     } else {

@@ -1,4 +1,5 @@
-// tcgen05 / TMA / mbarrier building blocks shared by the tensor-core kernels (pwconv_tc.cu, mbconv_fused.cu).
+// tcgen05 / TMA / mbarrier building blocks shared by the tensor-core kernels (pwconv_tc.cu, pwconv_ts.cu) and the
+// TMA depthwise kernel (dwconv_tma.cu).
 // Plain inline PTX for sm_100a; see DESIGN.md section 4 for how the kernels use them.
 #pragma once
 #include "yr_common.cuh"

@@ -118,7 +118,6 @@ int launch_resample(const yr_op& op, cudaStream_t s);
 int launch_rfcr(const yr_op& op, cudaStream_t s);
 int launch_se(const yr_op& op, cudaStream_t s);
 int launch_se_fc(const yr_op& op, cudaStream_t s);
-int launch_mbconv(const yr_op& op, cudaStream_t s);
 int dw_se_slots(const yr_op& op);
 bool dw_uses_tma(const yr_op& op);
 int dw_tma_se_slots(const yr_op& op);

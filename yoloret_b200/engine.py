@@ -61,7 +61,7 @@ class Engine:
                  weights: Dict[str, np.ndarray], anchors: np.ndarray, micro_batch: Optional[int] = None,
                  num_scales: int = 3, max_boxes: int = 20, cand_cap: Optional[int] = None,
                  device: Optional[torch.device] = None, pw_variant: int = _lib.PW_AUTO, input_u8: bool = False,
-                 fuse_se: bool = True, fuse_mbconv: bool = False, lanes: int = 1, autotune: bool = True, fuse_up2: bool = True,
+                 fuse_se: bool = True, lanes: int = 1, autotune: bool = True, fuse_up2: bool = True,
                  num_anchors: int = 3, fuse_dwpw: bool = True, fold_linear: bool = True):
         if not torch.cuda.is_available():
             raise _lib.YrError("yoloret_b200.Engine needs a CUDA device (no CPU fallback exists)")
@@ -73,11 +73,11 @@ class Engine:
             self.device = torch.device("cuda", torch.cuda.current_device())
         with torch.cuda.device(self.device):  # allocations, attribute caches and the autotuner run on that GPU
             self._init(model_name, num_classes, input_hw, batch, weights, anchors, micro_batch, num_scales, max_boxes,
-                       cand_cap, pw_variant, input_u8, fuse_se, fuse_mbconv, lanes, autotune, fuse_up2, num_anchors, fuse_dwpw,
+                       cand_cap, pw_variant, input_u8, fuse_se, lanes, autotune, fuse_up2, num_anchors, fuse_dwpw,
                        fold_linear)
 
     def _init(self, model_name, num_classes, input_hw, batch, weights, anchors, micro_batch, num_scales, max_boxes,
-              cand_cap, pw_variant, input_u8, fuse_se, fuse_mbconv, lanes, autotune, fuse_up2, num_anchors, fuse_dwpw=True, fold_linear=True):
+              cand_cap, pw_variant, input_u8, fuse_se, lanes, autotune, fuse_up2, num_anchors, fuse_dwpw=True, fold_linear=True):
         # the reference derives anchors per scale as num_anchors // num_scales (code/yolo.py:214-216); decode, the head
         # width and the y_true layout of this engine are written for 3 per scale (every shipped anchor file: 9 / 3)
         if int(num_anchors) != 3:
@@ -103,7 +103,6 @@ class Engine:
         self.input_u8 = input_u8
         self.pw_variant = pw_variant
         self.fuse_se = fuse_se
-        self.fuse_mbconv = fuse_mbconv
         self.autotune = bool(autotune)
         self.fuse_up2 = bool(fuse_up2)
         self.fuse_dwpw = bool(fuse_dwpw)
@@ -216,48 +215,9 @@ class Engine:
                         for cn, v in zip(L.extra["convs"], L.inp)]
                 mat = _pad_cols(np.concatenate(mats, 0), L.out.C)
                 self.wdev[i] = (self._dev(mat), self._dev(w["weighted_sum/alpha"]))
-        self._find_fused_blocks()
         self._find_dwpw_pairs()
         torch.cuda.synchronize(self.device)
         self.weight_bytes = sum(a.numel() * 4 + b.numel() * 4 for a, b in self.wdev.values())
-
-    def _find_fused_blocks(self):
-        """Inverted-residual blocks (1x1 expand+ReLU6 -> 3x3 depthwise+ReLU6 -> linear 1x1 project [+ add]) whose
-        channels fit the fused kernel run as ONE yr_op (YR_OP_MBCONV); their weight blobs are packed here.
-        Opt-in (``fuse_mbconv=True``): bit-identical to the three separate ops, but measured SLOWER at batch 64 on
-        B200 (the fused kernel is shared-memory-bandwidth bound, the separate ops stream HBM at 3.6-6 TB/s;
-        DESIGN.md section 4)."""
-        self.mb_blob: Dict[int, torch.Tensor] = {}
-        if not self.fuse_mbconv or self.pw_variant == _lib.PW_SIMT:
-            return
-        Ls = self.net.layers
-        consumers: Dict[str, int] = {}
-        for L in Ls:
-            for v in L.inp + ([L.res] if L.res is not None else []):
-                consumers[v.buf.name] = consumers.get(v.buf.name, 0) + 1
-        for i in range(len(Ls) - 2):
-            a, d, b = Ls[i], Ls[i + 1], Ls[i + 2]
-            ok = (a.kind == "pw" and a.act == "relu6" and a.res is None and a.gate is None
-                  and d.kind == "dw" and d.k == 3 and d.act == "relu6" and d.inp[0].buf is a.out.buf and d.inp[0].off == a.out.off
-                  and b.kind == "pw" and b.act == "none" and b.gate is None and b.inp[0].buf is d.out.buf
-                  and b.inp[0].off == d.out.off and not self.se_fused.get(i + 2)
-                  and consumers.get(a.out.buf.name, 0) == 1 and consumers.get(d.out.buf.name, 0) == 1
-                  and a.out.buf.ld == a.out.C and d.out.buf.ld == d.out.C)
-            if not ok:
-                continue
-            cin, ce, cout = a.inp[0].C, a.out.C, b.out.C
-            n = int(self.lib.yr_mbconv_packed_floats(cin, ce, cout))
-            if n <= 0:
-                continue
-            blob = torch.zeros(n, dtype=torch.float32, device=self.device)
-            w1, b1 = self.wdev[i]
-            wd, b2 = self.wdev[i + 1]
-            w2, b3 = self.wdev[i + 2]
-            _lib.check(self.lib.yr_mbconv_pack(w1.data_ptr(), int(w1.shape[1]), b1.data_ptr(), wd.data_ptr(),
-                                               int(wd.shape[1]), b2.data_ptr(), w2.data_ptr(), int(w2.shape[1]),
-                                               b3.data_ptr(), cin, ce, cout, blob.data_ptr(), self._stream()),
-                       "yr_mbconv_pack")
-            self.mb_blob[i] = blob
 
     def _layer_consumers(self) -> Dict[str, int]:
         if getattr(self, "_consumers", None) is None:
@@ -282,8 +242,6 @@ class Engine:
         cons = self._layer_consumers()
         for i in range(len(Ls) - 1):
             d, b = Ls[i], Ls[i + 1]
-            if i in self.mb_blob or (i - 1) in self.mb_blob:
-                continue
             ok = (d.kind == "dw" and d.k == 3 and d.stride in (1, 2) and b.kind == "pw" and b.gate is None
                   and b.inp[0].buf is d.out.buf and b.inp[0].off == d.out.off and b.inp[0].C == d.out.C
                   and cons.get(d.out.buf.name, 0) == 1 and not d.out.buf.full_batch and not self.se_fused.get(i + 1)
@@ -332,7 +290,7 @@ class Engine:
             return False
         if self._layer_consumers().get(a.out.buf.name, 0) != 1 or a.out.buf.full_batch:
             return False
-        return self._pw_variant_of(i) in (_lib.PW_TC, _lib.PW_TS) and i not in self.mb_blob and (i - 2) not in self.mb_blob
+        return self._pw_variant_of(i) in (_lib.PW_TC, _lib.PW_TS)
 
     def _pw_variant_of(self, i: int) -> int:
         """Kernel variant layer ``i`` runs with (explicit engine setting, else the autotuner's pick, else the
@@ -436,25 +394,6 @@ class Engine:
             o = ops[n_ops]
             n_ops += 1
             x = L.inp[0]
-            if i in self.mb_blob:
-                d, b = self.net.layers[i + 1], self.net.layers[i + 2]
-                o.kind = _lib.OP_MBCONV
-                o.B, o.H, o.W, o.C = nb, x.H, x.W, x.C
-                o.K2 = L.out.C
-                o.Ho, o.Wo, o.N = b.out.H, b.out.W, b.out.C
-                o.k, o.stride = 3, d.stride
-                o.pad_t, o.pad_l = d.extra.get("pad_t", 0), d.extra.get("pad_l", 0)
-                o.ld_in, o.ld_out = x.buf.ld, b.out.buf.ld
-                o.in_ = _ptr(x, chunk0, slot)
-                o.out = _ptr(b.out, chunk0)
-                o.w_tc = self.mb_blob[i].data_ptr()
-                if b.res is not None:
-                    o.res, o.ld_res = _ptr(b.res, chunk0), b.res.buf.ld
-                fused_bytes = 4 * (x.H * x.W * x.Clog + b.out.H * b.out.W * b.out.Clog * (2 if b.res is not None else 1)) \
-                    + self.mb_blob[i].numel() * 4
-                meta.append(("mbconv", L.name.replace("_expand", "") + "_fused", fused_bytes, L.flops + d.flops + b.flops, i))
-                skip = 2
-                continue
             if i in self.dwpw_blob:
                 b = self.net.layers[i + 1]
                 o.kind = _lib.OP_DWPW
