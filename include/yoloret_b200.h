@@ -112,7 +112,9 @@ typedef struct yr_op {
     int32_t K2, K3, K4;      /* RFCR: channels of in2..in4 */
     int32_t variant;         /* PW kernel choice: 0 = auto (tcgen05 when w_tc is given), 1 = SIMT fp32,
                                 2 = tcgen05 3xTF32, A and B operands in shared memory (w_tc = yr_pw_tc_pack image),
-                                3 = tcgen05 3xTF32, A operand in tensor memory (w_tc = yr_pw_ts_pack image) */
+                                3 = tcgen05 3xTF32, A operand in tensor memory (w_tc = yr_pw_ts_pack image),
+                                4 = the same as a CTA PAIR (cluster of 2, tcgen05.mma.cta_group::2, M = 256: each CTA holds half
+                                    of every weight tile; same yr_pw_ts_pack image; see yr_pw_ts2_supported) */
     const void* in;
     const void* in2;
     const void* in3;
@@ -148,6 +150,7 @@ int yr_pw_tc_pack(const float* w, int K, int N, float* packed, void* stream);
 /* Same for the variant-3 kernel (its n tiles are at most 192 columns wide, so the image differs). */
 int64_t yr_pw_ts_packed_floats(int K, int N);
 int yr_pw_ts_pack(const float* w, int K, int N, float* packed, void* stream);
+int yr_pw_ts2_supported(int K, int N); /* 1 when variant 4 (CTA pair) has a tiling for this layer */
 
 /* Fused depthwise -> pointwise pair (YR_OP_DWPW): w_pw [K][N] (the PW op's `w`), w_dw [9][K] + b_dw [K] (the DW op's
  * `w` / `bias`; K = the depthwise channel count = the 1x1 conv's input channels).  yr_dwpw_packed_floats returns 0

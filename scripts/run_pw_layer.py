@@ -25,7 +25,7 @@ op.B, op.H, op.W, op.C, op.Ho, op.Wo, op.N = B, H, W, K, H, W, N
 op.ld_in, op.ld_out = K, N
 op.in_, op.out, op.w, op.bias = a.data_ptr(), out.data_ptr(), w.data_ptr(), bias.data_ptr()
 if variant != 1:
-    packed = pack_tc(w, variant)
+    packed = pack_tc(w, variant)  # variant 4 (CTA pair) uses the variant-3 image
     op.w_tc = packed.data_ptr()
 ops = (YrOp * 1)(op)
 st = torch.cuda.current_stream().cuda_stream

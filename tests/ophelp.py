@@ -52,7 +52,7 @@ def pack_tc(w, variant=_lib.PW_TC):
     """W [K,N] (CUDA) -> the tensor-core weight image (yr_pw_tc_pack; yr_pw_ts_pack for variant 3)."""
     K, N = w.shape
     lib = _lib.lib()
-    sizer, packer = ((lib.yr_pw_ts_packed_floats, lib.yr_pw_ts_pack) if variant == _lib.PW_TS
+    sizer, packer = ((lib.yr_pw_ts_packed_floats, lib.yr_pw_ts_pack) if variant in (_lib.PW_TS, _lib.PW_TS2)
                      else (lib.yr_pw_tc_packed_floats, lib.yr_pw_tc_pack))
     n = int(sizer(K, N))
     assert n > 0, "no tensor-core tiling for K=%d N=%d" % (K, N)

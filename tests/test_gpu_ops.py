@@ -39,7 +39,7 @@ def _rand(*shape, seed=0, scale=1.0):
     (8, 40, 40, 432, 72, 432, "none", True, False),     # streamed weights over many k-blocks and tiles
     (6, 48, 48, 48, 32, 48, "swish", False, True),      # 4 narrow accumulators, SE gate, 108 tiles
 ])
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])   # 4 = the CTA-pair (cta_group::2) form of 3
 def test_pw_parity(built_lib, B, H, W, K, N, ld_in, act, use_res, use_scale, variant):
     a = _rand(B, H, W, ld_in, seed=1)
     w = _rand(K, N, seed=2, scale=K ** -0.5)
@@ -78,9 +78,11 @@ def test_pw_tensor_core_variants_bit_identical(built_lib, B, H, W, K, N, act, us
     o2 = pw_op(a, w, bias, act, res, scale, variant=2)
     o3 = pw_op(a, w, bias, act, res, scale, variant=3)
     assert torch.equal(o2, o3), float((o2 - o3).abs().max())
+    o4 = pw_op(a, w, bias, act, res, scale, variant=4)   # the CTA pair issues the same MMAs on 256-row tiles
+    assert torch.equal(o3, o4), float((o3 - o4).abs().max())
 
 
-@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("variant", [2, 3, 4])
 @pytest.mark.parametrize("B,H,W,K,N,act", [(3, 13, 13, 256, 256, "relu6"), (2, 26, 26, 256, 128, "relu6"), (2, 7, 5, 48, 48, "swish"),
                                            (5, 26, 26, 48, 96, "none")])
 def test_pw_fused_upsampling(built_lib, variant, B, H, W, K, N, act):
@@ -98,7 +100,7 @@ def test_pw_fused_upsampling(built_lib, variant, B, H, W, K, N, act):
     assert torch.isnan(fused[..., N:]).all()
 
 
-@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("variant", [2, 3, 4])
 @pytest.mark.parametrize("B,H,W,K,N", [(32, 26, 26, 256, 256), (64, 13, 13, 512, 256), (16, 52, 52, 128, 256)])
 def test_pw_streamed_weights_repeatable(built_lib, variant, B, H, W, K, N):
     """Wide layers stream their weight tiles through a shared-memory ring while the activation ring, the TMEM

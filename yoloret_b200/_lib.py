@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(HERE, "libyoloret_b200.so")
 ACT_NONE, ACT_RELU6, ACT_SWISH = 0, 1, 2
 OP_STEM, OP_PW, OP_DW, OP_RESAMPLE, OP_RFCR, OP_SE, OP_SE_FC, OP_DWPW = 0, 1, 2, 3, 4, 5, 6, 8
 UP2, POOL2, POOL4 = 0, 1, 2
-PW_AUTO, PW_SIMT, PW_TC, PW_TS = 0, 1, 2, 3
+PW_AUTO, PW_SIMT, PW_TC, PW_TS, PW_TS2 = 0, 1, 2, 3, 4
 
 
 class YrOp(C.Structure):
@@ -79,6 +79,7 @@ SYMBOLS = {
     "yr_pw_tc_pack": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "yr_pw_ts_packed_floats": (C.c_int64, [C.c_int, C.c_int]),
     "yr_pw_ts_pack": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
+    "yr_pw_ts2_supported": (C.c_int, [C.c_int, C.c_int]),
     "yr_dwpw_packed_floats": (C.c_int64, [C.c_int, C.c_int]),
     "yr_dwpw_pack": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "yr_dwpw_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -86,7 +86,8 @@ extern "C" int yr_run_ops(const yr_op* ops, int n_ops, void* stream) {
         switch (op.kind) {
             case YR_OP_STEM: rc = launch_stem(op, s); break;
             case YR_OP_PW:
-                if (op.variant == 3) rc = launch_pw_ts(op, s);
+                if (op.variant == 4) rc = launch_pw_ts2(op, s);
+                else if (op.variant == 3) rc = launch_pw_ts(op, s);
                 else rc = (op.variant == 2 || (op.variant == 0 && op.w_tc != nullptr)) ? launch_pw_tc(op, s) : launch_pw(op, s);
                 break;
             case YR_OP_DW: rc = launch_dw(op, s); break;

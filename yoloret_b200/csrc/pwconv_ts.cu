@@ -58,7 +58,7 @@ constexpr int EPI_LD = 36;
 constexpr int EPI_STAGE_BYTES = 4 * 32 * EPI_LD * 4;  // per epilogue group: 4 transpose buffers (+ the bias copy)
 constexpr int SMEM_LIMIT = 232448;
 constexpr int MAX_A = 12, MAX_T = 4, MAX_B = 32, MAX_ACC = 4;
-constexpr int BAR_BYTES = 1024;
+constexpr int BAR_BYTES = 2048;
 constexpr int T_STAGE_COLS = 64;  // hi columns [0,32), lo columns [32,64)
 
 struct Params {
@@ -92,7 +92,8 @@ constexpr int BAR_B_FULL = BAR_T_EMPTY + MAX_T;
 constexpr int BAR_B_EMPTY = BAR_B_FULL + MAX_B;
 constexpr int BAR_ACC_FULL = BAR_B_EMPTY + MAX_B;
 constexpr int BAR_ACC_EMPTY = BAR_ACC_FULL + MAX_ACC;
-constexpr int BAR_COUNT = BAR_ACC_EMPTY + MAX_ACC;
+constexpr int BAR_BP_FULL = BAR_ACC_EMPTY + MAX_ACC;  // CTA pair: the PEER's half of a weight slot has landed (leader's copy)
+constexpr int BAR_COUNT = BAR_BP_FULL + MAX_B;
 static_assert(BAR_COUNT * 8 + 8 <= BAR_BYTES, "barrier table overflows its reservation");
 
 constexpr int DBG_EV = 256;
@@ -126,6 +127,64 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+// ---- CTA pair (cta_group::2) helpers: the two CTAs of a cluster run ONE tcgen05.mma over 256 rows; each holds half of
+// every weight tile, so the per-CTA weight footprint halves (see the kernel comment) ----
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t cta) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_addr), "r"(cta));
+    return ra;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    // default semantics (release, CTA scope) as CUTLASS' ClusterBarrier::arrive(cta_id) uses: the payload is tensor memory, ordered by
+    // the tcgen05 fences; cluster-scope release/acquire would cost an L1 invalidate per k-block
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// waits of the leader on barriers that the peer CTA arrives on: cluster-scope acquire
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(0x989680u)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int what) {
+    for (uint32_t spins = 0; !mbar_try_wait_cluster(bar, parity); ++spins) {
+        if (spins > (1u << 12)) {
+            printf("yoloret_b200 pw_ts (CTA pair): mbarrier wait timed out (role %d, block %d, thread %d)\n", what, blockIdx.x,
+                   threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void umma_tf32_ts_2cta(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc,
+                                                  uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {  // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"((uint16_t)3)
+        : "memory");
+}
+
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
@@ -135,9 +194,10 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- epilogue (see pwconv_tc.cu for the access pattern; items here are m-major) ---------------
-template <int ACT, bool HAS_RES, bool UP2, bool DBG, bool SP = false>
+template <int ACT, bool HAS_RES, bool UP2, bool DBG, bool SP = false, int CG = 1>
 __device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, const float* s_bias, uint32_t tmem_base,
                                               uint32_t bar0, int item0, int item1, int q, int lane, int ewarp, int grp) {
+    const uint32_t crank = CG == 2 ? cluster_rank() : 0u;  // CTA pair: item = a PAIR of row blocks, this CTA takes one
     const int sub_r = lane >> 3;
     const int sub_c = (lane & 7) << 2;
     uint32_t it = 0;
@@ -146,7 +206,7 @@ __device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, const
     for (int item = item0; item < item1; ++item, ++it) {
         if (p.epi_groups == 1 ? grp == 0 : (int)(it & 1u) == grp) {
             const uint32_t acc = racc.slot;
-            const int row0 = mt * BM + q * 32;
+            const int row0 = (CG == 2 ? mt * 2 + (int)crank : mt) * BM + q * 32;
             const int ncols = min(p.BN, p.N - nt * p.BN);
             const int rows = SP ? 32 : min(32, p.M - row0);
             // depthwise front: tile row -> output pixel of the [B, Ho, Wo] tensor (-1 = outside the tile / image)
@@ -239,7 +299,8 @@ __device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, const
                 tc_fence_after();
             }
             tc_fence_before();
-            mbar_arrive(bar0 + 8u * (BAR_ACC_EMPTY + acc));
+            if (CG == 2) mbar_arrive_cluster(map_to_cta(bar0 + 8u * (BAR_ACC_EMPTY + acc), 0));  // the leader issues the MMAs
+            else mbar_arrive(bar0 + 8u * (BAR_ACC_EMPTY + acc));
             if (ewarp == 0 && lane == 0) dbg_mark(p, 7, it);
         }
         racc.advance(p.nAcc);
@@ -250,7 +311,7 @@ __device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, const
 // ---- converters: raw fp32 A tile (smem) -> (hi, lo) TF32 columns of a TMEM stage ----------------
 // Thread = tile row r = its TMEM lane.  The 128-byte row is read as 8 LDS.128 whose chunk index is
 // XORed with (r & 7) (the TMA swizzle): the 8 lanes of a quarter-warp hit 8 different bank groups.
-template <bool HAS_SCALE, bool DBG>
+template <bool HAS_SCALE, bool DBG, int CG = 1>
 __device__ __forceinline__ void converter_loop(const Params& p, const uint8_t* a_ring, uint32_t tmem_base, uint32_t bar0,
                                                int item0, int item1, int q, int lane, int grp) {
     Ring ra, rt;
@@ -268,7 +329,7 @@ __device__ __forceinline__ void converter_loop(const Params& p, const uint8_t* a
 #pragma unroll
                 for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(row + ((c ^ (r & 7)) << 4));
                 if (HAS_SCALE) {
-                    const int grow = mt * BM + r;
+                    const int grow = (CG == 2 ? mt * 2 + (int)cluster_rank() : mt) * BM + r;
                     if (grow < p.M) {
                         const float* g = p.scale + (size_t)(grow / p.rows_per_img) * p.K + kb * BK;
 #pragma unroll
@@ -308,7 +369,8 @@ __device__ __forceinline__ void converter_loop(const Params& p, const uint8_t* a
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(bar0 + 8u * (BAR_A_EMPTY + ra.slot));  // the raw tile has been consumed
-                    mbar_arrive(bar0 + 8u * (BAR_T_FULL + rt.slot));
+                    if (CG == 2) mbar_arrive_cluster(map_to_cta(bar0 + 8u * (BAR_T_FULL + rt.slot), 0));
+                    else mbar_arrive(bar0 + 8u * (BAR_T_FULL + rt.slot));
                 }
                 if (q == 0 && lane == 0) dbg_mark(p, 3, dq);
             }
@@ -462,9 +524,19 @@ __device__ __forceinline__ void dw_converter_loop(const Params& p, const uint8_t
     }
 }
 
-template <bool DBG, int FRONT>
+// CG = 2: the CTA-PAIR form (plain front only).  The two CTAs of a cluster process a PAIR of 128-row blocks with ONE
+// tcgen05.mma.cta_group::2 (M = 256) issued by the leader (cluster rank 0): each CTA converts its own rows into its own
+// tensor memory and drains its own accumulator rows, but holds only HALF of every weight tile (the rows of its half of
+// the n tile) - the per-CTA weight footprint halves, so layers whose (hi, lo) image does not fit one CTA's shared
+// memory become resident (K = 256, N = 128: 256 KB -> 128 KB per CTA) and streamed layers get twice the ring depth.
+// Cross-CTA signalling: the peer's converters and epilogue arrive on the LEADER's T_FULL / ACC_EMPTY barriers through
+// the cluster address space, the peer's otherwise idle MMA warp relays "my half of weight slot s has landed" to the
+// leader's BP_FULL barrier, and tcgen05.commit.cta_group::2 with a multicast mask releases T / B slots and publishes
+// the accumulator in both CTAs at once.
+template <bool DBG, int FRONT, int CG = 1>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
+    static_assert(CG == 1 || FRONT == 0, "the CTA-pair form exists for the plain front only");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [raw A ring: nA x 16K][weight slots: nB x (hi | lo)][epilogue: 2 x (transpose + bias)][barriers]
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -486,31 +558,42 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
             mbar_init(bar0 + 8u * (BAR_A_EMPTY + s), 4);
         }
         for (int s = 0; s < p.nT; ++s) {
-            mbar_init(bar0 + 8u * (BAR_T_FULL + s), 4);
+            mbar_init(bar0 + 8u * (BAR_T_FULL + s), 4 * CG);   // CTA pair: the leader's copy collects both CTAs' converters
             mbar_init(bar0 + 8u * (BAR_T_EMPTY + s), 1);
         }
         for (int s = 0; s < p.nB; ++s) {
             mbar_init(bar0 + 8u * (BAR_B_FULL + s), 1);
             mbar_init(bar0 + 8u * (BAR_B_EMPTY + s), 1);
+            if (CG == 2) mbar_init(bar0 + 8u * (BAR_BP_FULL + s), 1);
         }
         for (int s = 0; s < p.nAcc; ++s) {
             mbar_init(bar0 + 8u * (BAR_ACC_FULL + s), 1);
-            mbar_init(bar0 + 8u * (BAR_ACC_EMPTY + s), 128);
+            mbar_init(bar0 + 8u * (BAR_ACC_EMPTY + s), 128 * CG);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
-                     "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                         "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                         "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();  // both CTAs' barriers are initialised and both tensor memories allocated
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t crank = CG == 2 ? cluster_rank() : 0u;
 
-    const int item0 = blockIdx.x * p.items_per_cta;
+    // CTA pair: work is split over CLUSTERS (both CTAs walk the same items: pairs of row blocks x n tiles)
+    const int item0 = (CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x) * p.items_per_cta;
     const int item1 = min(item0 + p.items_per_cta, p.total_items);
 
     // Everything above touched only this CTA's shared/tensor memory.  The weight producer may start right away (the
@@ -551,7 +634,7 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
                                     bx, by, bimg);
                     else
                         tma_load_2d(base + a_off + ra.slot * p.a_slot_bytes, &tmA, bar0 + 8u * (BAR_A_FULL + ra.slot),
-                                    kb * BK, mt * BM);
+                                    kb * BK, (CG == 2 ? mt * 2 + (int)crank : mt) * BM);
                     dbg_mark(p, 0, dq++);
                     ra.advance(p.nA);
                 }
@@ -564,22 +647,34 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
             Ring rb;
             int nt = item0 % p.n_tiles;
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wp);
+            // one weight slot of the packed image = [hi tile: BN rows x 128 B | lo tile].  CTA pair: this CTA keeps rows
+            // [rank * BN/2, +BN/2) of both tiles: local slot = [hi half | lo half] (two bulk copies, one barrier)
+            const uint32_t g_slot = CG == 2 ? 2u * p.BN * 128u : b_slot_bytes;  // (depthwise front: + the taps behind the tiles)
+            const uint32_t half = p.BN * 64u;
+            auto load_slot = [&](uint32_t slot, int src_slot) {
+                const uint32_t bar = bar0 + 8u * (BAR_B_FULL + slot);
+                const uint32_t dst = base + b_off + slot * b_slot_bytes;
+                const uint8_t* src = wsrc + (size_t)src_slot * g_slot;
+                mbar_expect_tx(bar, b_slot_bytes);
+                if (CG == 2) {
+                    bulk_load(dst, src + crank * half, half, bar);
+                    bulk_load(dst + half, src + 2u * half + crank * half, half, bar);
+                } else {
+                    bulk_load(dst, src, b_slot_bytes, bar);
+                }
+            };
             if (p.resident) {  // the whole weight image once, first-needed slots first
                 const int total = p.n_tiles * p.KB;
                 for (int i = 0; i < total; ++i) {
                     int s = nt * p.KB + i;
                     if (s >= total) s -= total;
-                    mbar_expect_tx(bar0 + 8u * (BAR_B_FULL + s), b_slot_bytes);
-                    bulk_load(base + b_off + s * b_slot_bytes, wsrc + (size_t)s * b_slot_bytes, b_slot_bytes,
-                              bar0 + 8u * (BAR_B_FULL + s));
+                    load_slot((uint32_t)s, s);
                 }
             } else {
                 for (int item = item0; item < item1; ++item) {
                     for (int kb = 0; kb < p.KB; ++kb) {
                         mbar_wait(bar0 + 8u * (BAR_B_EMPTY + rb.slot), rb.phase ^ 1u, 0);
-                        mbar_expect_tx(bar0 + 8u * (BAR_B_FULL + rb.slot), b_slot_bytes);
-                        bulk_load(base + b_off + rb.slot * b_slot_bytes, wsrc + (size_t)(nt * p.KB + kb) * b_slot_bytes,
-                                  b_slot_bytes, bar0 + 8u * (BAR_B_FULL + rb.slot));
+                        load_slot(rb.slot, nt * p.KB + kb);
                         rb.advance(p.nB);
                     }
                     if (++nt == p.n_tiles) nt = 0;
@@ -593,8 +688,34 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
         const uint64_t desc0 = make_desc_sw128(base);
         const int k_tail = (p.K - (p.KB - 1) * BK + 7) / 8;
         int nt = item0 % p.n_tiles;
+        if (CG == 2 && crank != 0) {
+            // ----- peer CTA of a pair: no MMAs to issue; this warp relays "my half of weight slot s has landed" to the
+            // leader, in the order the leader consumes the slots -----
+            for (int item = item0; item < item1; ++item) {
+                for (int kb = 0; kb < p.KB; ++kb) {
+                    uint32_t slot;
+                    bool relay = true;
+                    if (p.resident) {
+                        slot = (uint32_t)(nt * p.KB + kb);
+                        relay = !((b_seen >> slot) & 1u);
+                        if (relay) {
+                            mbar_wait(bar0 + 8u * (BAR_B_FULL + slot), 0, 3);
+                            b_seen |= 1u << slot;
+                        }
+                    } else {
+                        slot = rb.slot;
+                        mbar_wait(bar0 + 8u * (BAR_B_FULL + slot), rb.phase, 3);
+                        rb.advance(p.nB);
+                    }
+                    if (relay && lane == 0) mbar_arrive_cluster(map_to_cta(bar0 + 8u * (BAR_BP_FULL + slot), 0));
+                    __syncwarp();
+                }
+                if (++nt == p.n_tiles) nt = 0;
+            }
+        } else {
         for (int item = item0; item < item1; ++item) {
-            mbar_wait(bar0 + 8u * (BAR_ACC_EMPTY + racc.slot), racc.phase ^ 1u, 2);
+            if (CG == 2) mbar_wait_cluster(bar0 + 8u * (BAR_ACC_EMPTY + racc.slot), racc.phase ^ 1u, 2);
+            else mbar_wait(bar0 + 8u * (BAR_ACC_EMPTY + racc.slot), racc.phase ^ 1u, 2);
             const uint32_t d_tmem = tmem_base + racc.slot * (uint32_t)p.acc_stride;
             for (int kb = 0; kb < p.KB; ++kb, ++dq) {
                 uint32_t slot;
@@ -602,17 +723,20 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
                     slot = (uint32_t)(nt * p.KB + kb);
                     if (!((b_seen >> slot) & 1u)) {  // a resident slot lands once: no barrier round trip after that
                         mbar_wait(bar0 + 8u * (BAR_B_FULL + slot), 0, 3);
+                        if (CG == 2) mbar_wait_cluster(bar0 + 8u * (BAR_BP_FULL + slot), 0, 3);
                         b_seen |= 1u << slot;
                     }
                 } else {
                     slot = rb.slot;
                     mbar_wait(bar0 + 8u * (BAR_B_FULL + slot), rb.phase, 3);
+                    if (CG == 2) mbar_wait_cluster(bar0 + 8u * (BAR_BP_FULL + slot), rb.phase, 3);
                     rb.advance(p.nB);
                 }
                 const uint64_t dbh = desc0 + ((b_off + slot * b_slot_bytes) >> 4);
-                const uint64_t dbl = dbh + ((p.BN * 128u) >> 4);
+                const uint64_t dbl = dbh + ((CG == 2 ? p.BN * 64u : p.BN * 128u) >> 4);  // CTA pair: half tiles per CTA
                 const int ksteps = (kb == p.KB - 1) ? k_tail : BK / 8;
-                mbar_wait(bar0 + 8u * (BAR_T_FULL + rt.slot), rt.phase, 4);
+                if (CG == 2) mbar_wait_cluster(bar0 + 8u * (BAR_T_FULL + rt.slot), rt.phase, 4);
+                else mbar_wait(bar0 + 8u * (BAR_T_FULL + rt.slot), rt.phase, 4);
                 tc_fence_after();
                 if (lane == 0) dbg_mark(p, 4, dq);
                 const uint32_t a_hi = tmem_base + (uint32_t)p.a_col0 + rt.slot * (uint32_t)T_STAGE_COLS;
@@ -621,13 +745,25 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
                     for (int k8 = 0; k8 < ksteps; ++k8) {
                         const uint64_t ko = (uint64_t)(k8 * 2);  // 32 bytes of K per step in the weight tile
                         const uint32_t ka = (uint32_t)(k8 * 8);  // 8 TMEM columns of K per step
-                        umma_tf32_ts(d_tmem, a_lo + ka, dbh + ko, p.idesc, (kb | k8) ? 1u : 0u);  // small terms first
-                        umma_tf32_ts(d_tmem, a_hi + ka, dbl + ko, p.idesc, 1u);
-                        umma_tf32_ts(d_tmem, a_hi + ka, dbh + ko, p.idesc, 1u);
+                        if (CG == 2) {
+                            umma_tf32_ts_2cta(d_tmem, a_lo + ka, dbh + ko, p.idesc, (kb | k8) ? 1u : 0u);
+                            umma_tf32_ts_2cta(d_tmem, a_hi + ka, dbl + ko, p.idesc, 1u);
+                            umma_tf32_ts_2cta(d_tmem, a_hi + ka, dbh + ko, p.idesc, 1u);
+                        } else {
+                            umma_tf32_ts(d_tmem, a_lo + ka, dbh + ko, p.idesc, (kb | k8) ? 1u : 0u);  // small terms first
+                            umma_tf32_ts(d_tmem, a_hi + ka, dbl + ko, p.idesc, 1u);
+                            umma_tf32_ts(d_tmem, a_hi + ka, dbh + ko, p.idesc, 1u);
+                        }
                     }
-                    umma_commit(bar0 + 8u * (BAR_T_EMPTY + rt.slot));
-                    if (!p.resident) umma_commit(bar0 + 8u * (BAR_B_EMPTY + slot));
-                    if (kb == p.KB - 1) umma_commit(bar0 + 8u * (BAR_ACC_FULL + racc.slot));
+                    if (CG == 2) {
+                        umma_commit_2cta(bar0 + 8u * (BAR_T_EMPTY + rt.slot));
+                        if (!p.resident) umma_commit_2cta(bar0 + 8u * (BAR_B_EMPTY + slot));
+                        if (kb == p.KB - 1) umma_commit_2cta(bar0 + 8u * (BAR_ACC_FULL + racc.slot));
+                    } else {
+                        umma_commit(bar0 + 8u * (BAR_T_EMPTY + rt.slot));
+                        if (!p.resident) umma_commit(bar0 + 8u * (BAR_B_EMPTY + slot));
+                        if (kb == p.KB - 1) umma_commit(bar0 + 8u * (BAR_ACC_FULL + racc.slot));
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) dbg_mark(p, 5, dq);
@@ -636,14 +772,15 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
             racc.advance(p.nAcc);
             if (++nt == p.n_tiles) nt = 0;
         }
+        }
     } else if (warp < 2 + NUM_CONVERTERS / 32) {
         const int cw = warp - 2;
         if constexpr (FRONT != 0)
             dw_converter_loop<FRONT ? FRONT : 1, DBG>(p, gbase + a_off, gbase + b_off,
                                                        reinterpret_cast<float*>(gbase + stage_off + (cw >> 2) * A_TILE_BYTES), tmem_base,
                                                        bar0, item0, item1, warp & 3, lane, cw >> 2);
-        else if (p.scale != nullptr) converter_loop<true, DBG>(p, gbase + a_off, tmem_base, bar0, item0, item1, warp & 3, lane, cw >> 2);
-        else converter_loop<false, DBG>(p, gbase + a_off, tmem_base, bar0, item0, item1, warp & 3, lane, cw >> 2);
+        else if (p.scale != nullptr) converter_loop<true, DBG, CG>(p, gbase + a_off, tmem_base, bar0, item0, item1, warp & 3, lane, cw >> 2);
+        else converter_loop<false, DBG, CG>(p, gbase + a_off, tmem_base, bar0, item0, item1, warp & 3, lane, cw >> 2);
     } else if (warp < 2 + (NUM_CONVERTERS + NUM_EPILOGUE) / 32) {
         // ===== epilogue =====
         const int ew8 = warp - (2 + NUM_CONVERTERS / 32);
@@ -663,7 +800,7 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
         asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
         const bool has_res = p.res != nullptr;
 #define YR_EPI(ACT_, RES_, UP_, SP_) \
-    epilogue_loop<ACT_, RES_, UP_, DBG, SP_>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg)
+    epilogue_loop<ACT_, RES_, UP_, DBG, SP_, CG>(p, stg, s_bias, tmem_base, bar0, item0, item1, warp & 3, lane, ew, eg)
         if constexpr (FRONT != 0) {  // depthwise front: rows are pixels of a spatial tile (no fused upsampling here)
             switch (p.act) {
                 case YR_ACT_RELU6:
@@ -699,8 +836,10 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
 
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();  // neither CTA leaves (or frees tensor memory) while the pair's MMAs may touch it
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -802,6 +941,38 @@ static bool make_tiling(int K, int N, Tiling& t) {
     na &= ~1ll;
     if (na < 2) return false;
     t.nA = (int)na;
+    t.smem = (size_t)(fixed + t.nA * tile + t.nB * slot);
+    return t.smem <= (size_t)SMEM_LIMIT;
+}
+
+// CTA-pair form: same n tiles / k blocks / TMEM geometry (and the same packed weight image) as make_tiling, but a CTA
+// holds half of every weight slot, so twice as much of the image fits (resident up to 2 x the single-CTA limit) and a
+// streamed ring is twice as deep for the same bytes.
+static bool make_tiling_pair(int K, int N, Tiling& t) {
+    if (!make_tiling(K, N, t)) return false;
+    if (t.BN % 16) return false;  // each CTA's half tile must be whole 8-row swizzle atoms
+    const long long slot = (long long)t.BN * 128;  // [hi half | lo half]
+    const long long tile = A_TILE_BYTES;
+    const long long fixed = 1024 + 2ll * t.epi_group_bytes + BAR_BYTES;
+    const long long avail = SMEM_LIMIT - fixed;
+    const long long wbytes = (long long)t.n_tiles * t.KB * slot;
+    if (t.n_tiles * t.KB <= MAX_B && wbytes + 4 * tile <= avail) {
+        t.resident = 1;
+        t.nB = t.n_tiles * t.KB;
+    } else {
+        t.resident = 0;
+        long long nb = (avail - 4 * tile) / slot;
+        if (nb > 8) nb = 8;
+        if (nb > (long long)t.n_tiles * t.KB) nb = (long long)t.n_tiles * t.KB;
+        if (nb < 2) return false;
+        t.nB = (int)nb;
+    }
+    long long na = (avail - t.nB * slot) / tile;
+    if (na > MAX_A) na = MAX_A;
+    na &= ~1ll;
+    if (na < 2) return false;
+    t.nA = (int)na;
+    t.b_slot = (uint32_t)slot;
     t.smem = (size_t)(fixed + t.nA * tile + t.nB * slot);
     return t.smem <= (size_t)SMEM_LIMIT;
 }
@@ -1012,7 +1183,8 @@ int launch_dwpw(const yr_op& op, cudaStream_t s) {
     return YR_OK;
 }
 
-int launch_pw_ts(const yr_op& op, cudaStream_t s) {
+template <int CG>
+static int launch_pw_ts_cg(const yr_op& op, cudaStream_t s) {
     YR_CHECK_ARG(op.in && op.out && op.w_tc && op.bias, "pw_ts: null pointer (w_tc = yr_pw_ts_pack output)");
     YR_CHECK_ARG(op.C > 0 && op.C % 8 == 0 && op.N > 0 && op.N % 8 == 0, "pw_ts: K=%d N=%d must be multiples of 8", op.C,
                  op.N);
@@ -1027,8 +1199,8 @@ int launch_pw_ts(const yr_op& op, cudaStream_t s) {
                  "pw_ts: output must be HxW, or 2Hx2W (fused nearest upsampling, no residual): got %dx%d for %dx%d", op.Ho, op.Wo,
                  op.H, op.W);
     ts::Tiling t;
-    if (!ts::make_tiling(op.C, op.N, t)) {
-        set_error("pw_ts: no tiling for K=%d N=%d", op.C, op.N);
+    if (!(CG == 2 ? ts::make_tiling_pair(op.C, op.N, t) : ts::make_tiling(op.C, op.N, t))) {
+        set_error("pw_ts: no tiling for K=%d N=%d (cta_group %d)", op.C, op.N, CG);
         return YR_ERR_UNSUPPORTED;
     }
     tc::EncodeTiledFn enc = tc::encode_tiled();
@@ -1075,9 +1247,9 @@ int launch_pw_ts(const yr_op& op, cudaStream_t s) {
     p.acc_stride = t.acc_stride;
     p.a_col0 = t.a_col0;
     p.epi_group_bytes = t.epi_group_bytes;
-    p.total_items = p.n_tiles * p.m_tiles;
+    p.total_items = p.n_tiles * (CG == 2 ? (p.m_tiles + 1) / 2 : p.m_tiles);  // CTA pair: items are PAIRS of row blocks
     p.a_slot_bytes = ts::A_TILE_BYTES;
-    p.b_slot_bytes = 2u * t.BN * 128u;
+    p.b_slot_bytes = CG == 2 ? t.b_slot : 2u * t.BN * 128u;
     p.TH = p.TW = p.IW = p.tiles_h = p.tiles_w = 1;
     p.Ho = p.Wo = p.pad_t = p.pad_l = p.dw_act = 0;
     p.epi_groups = 2;
@@ -1085,22 +1257,22 @@ int launch_pw_ts(const yr_op& op, cudaStream_t s) {
     static DeviceOnce attr_once;  // function attributes are per device
     bool& attr_set = attr_once.cur();
     if (!attr_set) {
-        if (cudaFuncSetAttribute(ts::pw_ts_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM_LIMIT) !=
+        if (cudaFuncSetAttribute(ts::pw_ts_kernel<false, 0, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM_LIMIT) !=
                 cudaSuccess ||
-            cudaFuncSetAttribute(ts::pw_ts_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM_LIMIT) !=
+            cudaFuncSetAttribute(ts::pw_ts_kernel<true, 0, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM_LIMIT) !=
                 cudaSuccess) {
             set_error("pw_ts: cannot raise the dynamic shared memory limit: %s", cudaGetErrorString(cudaGetLastError()));
             return YR_ERR_CUDA;
         }
         attr_set = true;
     }
-    const int max_ctas = tc::num_sms();
+    const int max_ctas = tc::num_sms() / CG;  // CTA pair: work units are clusters of two CTAs
     // contiguous runs of m-major items per CTA: the n tiles of a 128-row block are mostly on one SM (the A re-read hits
     // L2 either way), and the split is item- not block-granular, which fills more SMs when there are few row blocks
     // (26x26 x 64 images = 338 blocks x 2 n tiles: 136 CTAs x 5 items instead of 113 x 6)
     p.items_per_cta = (p.total_items + max_ctas - 1) / max_ctas;
-    const int grid = (p.total_items + p.items_per_cta - 1) / p.items_per_cta;
-    p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(t.BN >> 3) << 17) | ((uint32_t)(ts::BM >> 4) << 24);
+    const int grid = CG * ((p.total_items + p.items_per_cta - 1) / p.items_per_cta);
+    p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(t.BN >> 3) << 17) | ((uint32_t)((CG * ts::BM) >> 4) << 24);
     p.dbg = nullptr;
     p.dbg_skip = 0;
     static const bool debug = getenv("YR_PW_TC_DEBUG") != nullptr;  // developer aid only: timeline of CTA 0
@@ -1110,12 +1282,31 @@ int launch_pw_ts(const yr_op& op, cudaStream_t s) {
         cudaMemsetAsync(dbuf, 0, 8 * ts::DBG_EV * sizeof(long long), s);
         p.dbg = dbuf;
     }
-    if (launch_pdl(debug ? ts::pw_ts_kernel<true, 0> : ts::pw_ts_kernel<false, 0>, dim3(grid), dim3(ts::NUM_THREADS), t.smem, s, tm,
-                   p) != cudaSuccess) {
+    if (CG == 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(ts::NUM_THREADS);
+        cfg.dynamicSmemBytes = t.smem;
+        cfg.stream = s;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = pdl_enabled() ? 2 : 1;
+        if (cudaLaunchKernelEx(&cfg, ts::pw_ts_kernel<false, 0, CG>, tm, p) != cudaSuccess) {
+            set_error("pw_ts (CTA pair): launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return YR_ERR_CUDA;
+        }
+    } else if (launch_pdl(debug ? ts::pw_ts_kernel<true, 0, CG> : ts::pw_ts_kernel<false, 0, CG>, dim3(grid), dim3(ts::NUM_THREADS),
+                          t.smem, s, tm, p) != cudaSuccess) {
         set_error("pw_ts: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         return YR_ERR_CUDA;
     }
-    if (debug) {
+    if (debug && CG == 1) {
         static long long h[8 * ts::DBG_EV];
         cudaStreamSynchronize(s);
         cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
@@ -1133,9 +1324,18 @@ int launch_pw_ts(const yr_op& op, cudaStream_t s) {
     return YR_OK;
 }
 
+int launch_pw_ts(const yr_op& op, cudaStream_t s) { return launch_pw_ts_cg<1>(op, s); }
+int launch_pw_ts2(const yr_op& op, cudaStream_t s) { return launch_pw_ts_cg<2>(op, s); }
+
 }  // namespace yr
 
 using namespace yr;
+
+/* 1 when the CTA-pair kernel (variant 4) has a tiling for a K x N layer (same weight image as variant 3). */
+extern "C" int yr_pw_ts2_supported(int K, int N) {
+    ts::Tiling t;
+    return ts::make_tiling_pair(K, N, t) ? 1 : 0;
+}
 
 extern "C" int64_t yr_pw_ts_packed_floats(int K, int N) {
     ts::Tiling t;

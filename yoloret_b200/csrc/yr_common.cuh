@@ -112,6 +112,7 @@ int launch_stem(const yr_op& op, cudaStream_t s);
 int launch_pw(const yr_op& op, cudaStream_t s);
 int launch_pw_tc(const yr_op& op, cudaStream_t s);
 int launch_pw_ts(const yr_op& op, cudaStream_t s);
+int launch_pw_ts2(const yr_op& op, cudaStream_t s);
 int launch_dwpw(const yr_op& op, cudaStream_t s);
 int launch_dw(const yr_op& op, cudaStream_t s);
 int launch_resample(const yr_op& op, cudaStream_t s);
