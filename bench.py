@@ -420,7 +420,7 @@ def run_b200(a):
 
     picks = {}
     for i, v in sorted(eng.pw_choice.items()):
-        picks[eng.net.layers[i].name] = {_lib.PW_TC: "tc", _lib.PW_TS: "ts"}.get(v, str(v))
+        picks[eng.net.layers[i].name] = {_lib.PW_TC: "tc", _lib.PW_TS: "ts", _lib.PW_TS2: "ts2"}.get(v, str(v))
     out = {
         "metric": METRIC if a.size == 416 else "images/sec at %dx%d" % (a.size, a.size), "value": value, "unit": UNIT,
         "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
@@ -448,6 +448,7 @@ def run_b200(a):
         "clocks": clocks,
         "verified": verified, "verify": verify_report, "multi_gpu_equivalence": equivalence,
         "pw_kernel_picks": {"tc": sum(1 for v in picks.values() if v == "tc"), "ts": sum(1 for v in picks.values() if v == "ts"),
+                            "ts2_cta_pair": sum(1 for v in picks.values() if v == "ts2"),
                             "per_layer": picks},
     }
 

@@ -24,7 +24,7 @@ TOL = 1e-3
 # implementations already differ by ~1e-3 absolute there (scripts/diag_parity.py: the fp32 oracle itself is
 # 3-5e-4 from an fp64 run).  They are held to a tolerance relative to the tensor's scale: 1e-4 x max|ref| for
 # the exact-fp32 SIMT pointwise variant, 3e-4 x for the tcgen05 3xTF32 variant (~21 mantissa bits per product).
-LOGIT_REL = {0: 3e-4, 1: 1e-4, 2: 3e-4, 3: 3e-4}  # 0 = autotuned mix of the two tcgen05 kernels
+LOGIT_REL = {0: 3e-4, 1: 1e-4, 2: 3e-4, 3: 3e-4, 4: 3e-4}  # 0 = autotuned mix of the tcgen05 kernels, 4 = CTA-pair form
 
 
 def _logits_close(a, r, variant, what=""):
@@ -45,7 +45,7 @@ def _golden_weights():
     ("efficientnetb3", 80, (64, 96), 2, None),
     ("efficientnetlite0", 80, (64, 64), 2, 1),
 ])
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 def test_network_matches_oracle(built_lib, anchors, name, ncls, hw, B, micro, variant):
     nd = NetDef(name, ncls, hw)
     w = synthetic_weights(nd.weight_shapes, ncls, seed=11)

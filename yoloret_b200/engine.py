@@ -184,7 +184,7 @@ class Engine:
                 self.wdev[i] = (self._dev(mat), self._dev(_pad_cols(b, L.out.C)))
                 if self.pw_variant in (_lib.PW_AUTO, _lib.PW_TC):
                     self.wtc[i] = self._pack_tc(self.wdev[i][0], _lib.PW_TC)
-                if self.pw_variant in (_lib.PW_AUTO, _lib.PW_TS):
+                if self.pw_variant in (_lib.PW_AUTO, _lib.PW_TS, _lib.PW_TS2):
                     self.wts[i] = self._pack_tc(self.wdev[i][0], _lib.PW_TS)
             elif L.kind == "dw":
                 k = w[L.conv + "/depthwise_kernel"][:, :, :, 0].astype(np.float64)  # [k,k,C]
@@ -290,11 +290,15 @@ class Engine:
             return False
         if self._layer_consumers().get(a.out.buf.name, 0) != 1 or a.out.buf.full_batch:
             return False
-        return self._pw_variant_of(i) in (_lib.PW_TC, _lib.PW_TS)
+        return self._pw_variant_of(i) in (_lib.PW_TC, _lib.PW_TS, _lib.PW_TS2)
 
     def _pw_variant_of(self, i: int) -> int:
         """Kernel variant layer ``i`` runs with (explicit engine setting, else the autotuner's pick, else the
         first tensor-core kernel that has a tiling, else SIMT)."""
+        if self.pw_variant == _lib.PW_TS2:  # the CTA-pair form where it has a tiling, else the single-CTA form
+            L = self.net.layers[i]
+            ok = self.wts.get(i) is not None and self.lib.yr_pw_ts2_supported(L.inp[0].C, L.out.C)
+            return _lib.PW_TS2 if ok else (_lib.PW_TS if self.wts.get(i) is not None else _lib.PW_SIMT)
         if self.pw_variant != _lib.PW_AUTO:
             return self.pw_variant
         if i in self.pw_choice:
@@ -306,9 +310,10 @@ class Engine:
         return _lib.PW_SIMT
 
     def _autotune_pw(self, reps: int = 3):
-        """Picks, per pointwise layer, the faster of the two tcgen05 kernels (shared-memory A vs tensor-memory A)
-        by timing both on the layer's real buffers with CUDA events.  The two kernels issue the same MMAs in
-        the same order and give bit-identical outputs (tests/test_gpu_ops.py), so the pick changes speed only."""
+        """Picks, per pointwise layer, the fastest of the tcgen05 kernels (shared-memory A, tensor-memory A, and the
+        CTA-pair form of the latter) by timing them on the layer's real buffers with CUDA events.  They issue the
+        same MMAs in the same order and give bit-identical outputs (tests/test_gpu_ops.py), so the pick changes speed
+        only."""
         both = [i for i, L in enumerate(self.net.layers)
                 if L.kind == "pw" and self.wtc.get(i) is not None and self.wts.get(i) is not None]
         if not both:
@@ -328,18 +333,26 @@ class Engine:
             if key not in cache:
                 o = ops[op_of[i]]
                 t = {}
-                for v, img in ((_lib.PW_TC, self.wtc[i]), (_lib.PW_TS, self.wts[i])):
-                    o.variant, o.w_tc = v, img.data_ptr()
-                    _lib.check(self.lib.yr_run_ops(C.byref(o), 1, st), "yr_run_ops")
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                    for _ in range(reps):
+                cands = [(_lib.PW_TC, self.wtc[i]), (_lib.PW_TS, self.wts[i])]
+                if self.lib.yr_pw_ts2_supported(int(key[2]), int(key[3])):
+                    cands.append((_lib.PW_TS2, self.wts[i]))   # the CTA-pair form reads the same weight image
+                for rnd in range(2):  # two interleaved rounds, best time per kernel: less sensitive to what ran just before
+                    for v, img in cands:
+                        o.variant, o.w_tc = v, img.data_ptr()
                         _lib.check(self.lib.yr_run_ops(C.byref(o), 1, st), "yr_run_ops")
-                    e1.record()
-                    torch.cuda.synchronize(self.device)
-                    t[v] = e0.elapsed_time(e1) / reps
-                cache[key] = _lib.PW_TS if t[_lib.PW_TS] < t[_lib.PW_TC] else _lib.PW_TC
-                self.autotune_log.append((L.name, key[:4], round(t[_lib.PW_TC] * 1e3, 1), round(t[_lib.PW_TS] * 1e3, 1)))
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        for _ in range(reps):
+                            _lib.check(self.lib.yr_run_ops(C.byref(o), 1, st), "yr_run_ops")
+                        e1.record()
+                        torch.cuda.synchronize(self.device)
+                        t[v] = min(t.get(v, 1e9), e0.elapsed_time(e1) / reps)
+                # hysteresis: leave the default (tensor-memory A, one CTA) only for a kernel that is clearly faster, so
+                # run-to-run noise does not flip the picks (outputs are bit-identical either way)
+                best = min(t, key=lambda v: t[v])
+                cache[key] = best if t[best] < 0.98 * t[_lib.PW_TS] else _lib.PW_TS
+                self.autotune_log.append((L.name, key[:4]) + tuple(round(t.get(v, 0.0) * 1e3, 1)
+                                                                    for v in (_lib.PW_TC, _lib.PW_TS, _lib.PW_TS2)))
             self.pw_choice[i] = cache[key]
         self._plans.clear()  # plans were built with the provisional variants
 
@@ -434,7 +447,7 @@ class Engine:
             elif L.kind == "pw":
                 o.kind = _lib.OP_PW
                 o.variant = self._pw_variant_of(i)
-                img = (self.wts if o.variant == _lib.PW_TS else self.wtc).get(i)
+                img = (self.wts if o.variant in (_lib.PW_TS, _lib.PW_TS2) else self.wtc).get(i)
                 if o.variant != _lib.PW_SIMT and img is not None:
                     o.w_tc = img.data_ptr()
                 if L.res is not None:
