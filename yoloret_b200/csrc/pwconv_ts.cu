@@ -386,14 +386,15 @@ __device__ __forceinline__ void converter_loop(const Params& p, const uint8_t* a
 //   1. register-tiled depthwise conv exactly as dw_tma_kernel does it (thread = 4 channels x a 2 x 4 pixel patch:
 //      24 (stride 2: 45) LDS.128 of the box for 32 outputs, 8 lanes cover a 128-byte pixel = conflict-free; same
 //      operation order: acc = 0; acc = fma(x, w, acc) over (kh, kw) row-major; act(acc + bias)), results written to a
-//      16 KB staging tile [128 pixels][32 channels] whose 16-byte chunks are XOR-swizzled with (row & 7);
+//      16 KB staging tile [128 pixels][32 channels] - the head of the box's own ring slot, once the whole group has read
+//      the box - whose 16-byte chunks are XOR-swizzled with (row & 7);
 //   2. the plain converter: thread = tile row = TMEM lane reads its 128-byte row (8 conflict-free LDS.128), splits
 //      into (hi, lo) TF32 and writes tensor memory.
 // The taps and bias of the k-block ride in the tail of the weight slot.  Named barrier 3 + group fences the staging tile.
 template <int S, bool DBG>
 __device__ __forceinline__ void dw_converter_loop(const Params& p, const uint8_t* a_ring, const uint8_t* b_ring,
-                                                  float* stage, uint32_t tmem_base, uint32_t bar0, int item0, int item1,
-                                                  int q, int lane, int grp) {
+                                                  uint32_t tmem_base, uint32_t bar0, int item0, int item1, int q, int lane,
+                                                  int grp) {
     constexpr int PH = 2, PW = 4, KS = 3;
     constexpr int IN_ROWS = (PH - 1) * S + KS, IN_COLS = (PW - 1) * S + KS;
     Ring ra, rt, rb;
@@ -458,10 +459,10 @@ __device__ __forceinline__ void dw_converter_loop(const Params& p, const uint8_t
                     }
                 }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar0 + 8u * (BAR_A_EMPTY + ra.slot));  // this warp is done with the box
                 const float4 bv = wd[72];
-                // the staging tile may still be read by phase 2 of this group's previous k-block
+                // the staging tile is the head of this box's OWN slot: every warp of the group must be done reading the
+                // box before anyone overwrites it (no separate staging buffers: their 16 KB per group go to the A ring)
+                float* stage = reinterpret_cast<float*>(const_cast<uint8_t*>(a_ring) + (size_t)ra.slot * p.a_slot_bytes);
                 asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                 if (worker) {
 #pragma unroll
@@ -488,6 +489,9 @@ __device__ __forceinline__ void dw_converter_loop(const Params& p, const uint8_t
                         v[c] = live_row ? *reinterpret_cast<const float4*>(rowp + ((c ^ (gtid & 7)) << 2))
                                         : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+                fence_proxy_async();  // generic-proxy writes to the slot are ordered before the TMA that refills it
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar0 + 8u * (BAR_A_EMPTY + ra.slot));  // this warp is done with the slot
                 mbar_wait(bar0 + 8u * (BAR_T_EMPTY + rt.slot), rt.phase ^ 1u, 7);
                 tc_fence_after();
                 if (q == 0 && lane == 0) dbg_mark(p, 2, dq);
@@ -545,8 +549,8 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
     const uint32_t a_off = 0;
     const uint32_t b_off = a_off + p.nA * p.a_slot_bytes;
     const uint32_t epi_off = b_off + p.nB * b_slot_bytes;
-    const uint32_t stage_off = epi_off + (uint32_t)(p.epi_groups * p.epi_group_bytes);  // depthwise front: 2 staging tiles
-    const uint32_t bar_off = stage_off + (FRONT != 0 ? (uint32_t)p.conv_groups * (uint32_t)A_TILE_BYTES : 0u);
+    const uint32_t stage_off = epi_off + (uint32_t)(p.epi_groups * p.epi_group_bytes);
+    const uint32_t bar_off = stage_off;
     const uint32_t bar0 = base + bar_off;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gbase + bar_off + 8u * BAR_COUNT);
 
@@ -776,9 +780,8 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
     } else if (warp < 2 + NUM_CONVERTERS / 32) {
         const int cw = warp - 2;
         if constexpr (FRONT != 0)
-            dw_converter_loop<FRONT ? FRONT : 1, DBG>(p, gbase + a_off, gbase + b_off,
-                                                       reinterpret_cast<float*>(gbase + stage_off + (cw >> 2) * A_TILE_BYTES), tmem_base,
-                                                       bar0, item0, item1, warp & 3, lane, cw >> 2);
+            dw_converter_loop<FRONT ? FRONT : 1, DBG>(p, gbase + a_off, gbase + b_off, tmem_base, bar0, item0, item1, warp & 3, lane,
+                                                       cw >> 2);
         else if (p.scale != nullptr) converter_loop<true, DBG, CG>(p, gbase + a_off, tmem_base, bar0, item0, item1, warp & 3, lane, cw >> 2);
         else converter_loop<false, DBG, CG>(p, gbase + a_off, tmem_base, bar0, item0, item1, warp & 3, lane, cw >> 2);
     } else if (warp < 2 + (NUM_CONVERTERS + NUM_EPILOGUE) / 32) {
@@ -787,9 +790,8 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
         const int ew = ew8 & 3, eg = ew8 >> 2;
         if constexpr (FRONT != 0) {
             if (eg == 1 && p.conv_groups == 3) {  // third converter group (see Params::conv_groups)
-                dw_converter_loop<FRONT ? FRONT : 1, DBG>(p, gbase + a_off, gbase + b_off,
-                                                           reinterpret_cast<float*>(gbase + stage_off + 2 * A_TILE_BYTES), tmem_base,
-                                                           bar0, item0, item1, warp & 3, lane, 2);
+                dw_converter_loop<FRONT ? FRONT : 1, DBG>(p, gbase + a_off, gbase + b_off, tmem_base, bar0, item0, item1, warp & 3,
+                                                           lane, 2);
             }
         }
         float* stg = reinterpret_cast<float*>(gbase + epi_off + eg * p.epi_group_bytes) + ew * 32 * EPI_LD;
@@ -1012,12 +1014,18 @@ static bool make_tiling_dw(int K, int N, int S, int Ho, int Wo, Tiling& t) {
     static const int shapes[9][2] = {{8, 16}, {16, 8}, {4, 32}, {32, 4}, {2, 64}, {4, 16}, {8, 8}, {16, 4}, {2, 32}};
     long long best = -1;
     Tiling bt = t;
-    static const int groups_knob = [] {  // experiment knob: 3 turns the second epilogue group into a third converter
-        const char* e = getenv("YR_DWPW_GROUPS");  // group (stride 1).  Measured on B200: no gain (104x104x144 -> 24: 205 us
-        return e ? atoi(e) : 2;                    // either way; 208x208x24 -> 16: 238 vs 201 us), so the default is 2.
+    // A third converter group (the second epilogue group's warps) pays when the epilogue is light next to the depthwise
+    // work of a tile - many k-blocks, few output columns - and costs when it is not (one epilogue group then drains every
+    // tile).  Measured on B200 with the staging tile inside the A slot (ring of 6 boxes): 26x26x432->72 78 -> 68 us,
+    // 13x13x720->120 39 -> 36 us, 104x104x144->24 211 -> 209 us, but 52x52x144->48 80 -> 82 us and 208x208x24->16 199 -> 260 us.
+    static const int groups_knob = [] {  // experiment knob: 2 / 3 force the group count, 0 = the rule below
+        const char* e = getenv("YR_DWPW_GROUPS");
+        return e ? atoi(e) : 0;
     }();
+    const int g_rule = t.KB >= 4 * ((t.BN + 31) / 32) ? 3 : 2;
+    const int g_max = S == 1 ? (groups_knob == 2 || groups_knob == 3 ? groups_knob : g_rule) : 2;
     for (int i = 0; i < 9; ++i) {
-        for (int G = (S == 1 && groups_knob >= 3) ? 3 : 2; G >= 2; --G) {
+        for (int G = g_max; G >= 2; --G) {
             Tiling c = t;
             const int TH = shapes[i][0], TW = shapes[i][1];
             c.TH = TH; c.TW = TW;
@@ -1032,7 +1040,7 @@ static bool make_tiling_dw(int K, int N, int S, int Ho, int Wo, Tiling& t) {
             if (c.nT < G) continue;
             c.nT = c.nT / G * G;  // every ring is a multiple of the group count: a slot always belongs to one group,
                                   // which then sees every mbarrier phase of it (see make_tiling on even rings)
-            const long long fixed = 1024 + (long long)c.epi_groups * c.epi_group_bytes + (long long)G * A_TILE_BYTES + BAR_BYTES;
+            const long long fixed = 1024 + (long long)c.epi_groups * c.epi_group_bytes + BAR_BYTES;  // (staging tiles live in the A slots)
             const long long avail = SMEM_LIMIT - fixed;
             if (c.KB <= MAX_B && (long long)c.KB * c.b_slot + (long long)G * c.a_slot <= avail) {
                 c.resident = 1;
