@@ -38,11 +38,12 @@ dw_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ wgt
 #pragma unroll
     for (int i = 0; i < KS * KS; ++i) w[i] = ldg4(wgt + (size_t)i * C + c);
 
+    const float4 bv = ldg4(bias + c);
     float4 acc[TH][TW];
 #pragma unroll
     for (int t = 0; t < TH; ++t)
 #pragma unroll
-        for (int o = 0; o < TW; ++o) acc[t][o] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int o = 0; o < TW; ++o) acc[t][o] = bv;  // accumulate on top of the folded-BN bias (as dw_tma_kernel)
 
     const int hi0 = ho0 * S - pad_t;
     const int wi0 = wo0 * S - pad_l;
@@ -74,7 +75,6 @@ dw_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ wgt
         }
     }
 
-    const float4 bv = ldg4(bias + c);
 #pragma unroll
     for (int t = 0; t < TH; ++t) {
         const int ho = ho0 + t;
@@ -84,10 +84,10 @@ dw_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ wgt
             const int wo = wo0 + o;
             if (wo >= Wo) continue;
             float4 v;
-            v.x = apply_act<ACT>(acc[t][o].x + bv.x);
-            v.y = apply_act<ACT>(acc[t][o].y + bv.y);
-            v.z = apply_act<ACT>(acc[t][o].z + bv.z);
-            v.w = apply_act<ACT>(acc[t][o].w + bv.w);
+            v.x = apply_act<ACT>(acc[t][o].x);
+            v.y = apply_act<ACT>(acc[t][o].y);
+            v.z = apply_act<ACT>(acc[t][o].z);
+            v.w = apply_act<ACT>(acc[t][o].w);
             st4(out + (((size_t)b * Ho + ho) * Wo + wo) * ld_out + c, v);
             ps.x += v.x; ps.y += v.y; ps.z += v.z; ps.w += v.w;
         }

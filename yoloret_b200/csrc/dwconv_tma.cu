@@ -118,7 +118,7 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tm, const Params p) {
 #pragma unroll
             for (int t = 0; t < PH; ++t)
 #pragma unroll
-                for (int o = 0; o < PW; ++o) acc[t][o] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int o = 0; o < PW; ++o) acc[t][o] = bv;  // accumulate on top of the folded-BN bias
 #pragma unroll
             for (int rr = 0; rr < IN_ROWS; ++rr) {
                 float4 x[IN_COLS];
@@ -149,10 +149,10 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tm, const Params p) {
                     const int wo = wo0 + o;
                     if (wo >= p.Wo) continue;
                     float4 v;
-                    v.x = apply_act<ACT>(acc[t][o].x + bv.x);
-                    v.y = apply_act<ACT>(acc[t][o].y + bv.y);
-                    v.z = apply_act<ACT>(acc[t][o].z + bv.z);
-                    v.w = apply_act<ACT>(acc[t][o].w + bv.w);
+                    v.x = apply_act<ACT>(acc[t][o].x);
+                    v.y = apply_act<ACT>(acc[t][o].y);
+                    v.z = apply_act<ACT>(acc[t][o].z);
+                    v.w = apply_act<ACT>(acc[t][o].w);
                     st4(p.out + (((size_t)b * p.Ho + ho) * p.Wo + wo) * p.ld_out + c, v);
                     ps.x += v.x; ps.y += v.y; ps.z += v.z; ps.w += v.w;
                 }

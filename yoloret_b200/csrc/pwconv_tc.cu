@@ -235,8 +235,8 @@ __device__ __forceinline__ void converter_loop(const Params& p, uint8_t* gbase, 
                     for (int j = 0; j < 4; ++j) {
                         float4 h, l;
                         h.x = tf32_rna(v[j].x); h.y = tf32_rna(v[j].y); h.z = tf32_rna(v[j].z); h.w = tf32_rna(v[j].w);
-                        l.x = tf32_rna(v[j].x - h.x); l.y = tf32_rna(v[j].y - h.y);
-                        l.z = tf32_rna(v[j].z - h.z); l.w = tf32_rna(v[j].w - h.w);
+                        l.x = tf32_lo(v[j].x, h.x); l.y = tf32_lo(v[j].y, h.y);
+                        l.z = tf32_lo(v[j].z, h.z); l.w = tf32_lo(v[j].w, h.w);
                         hi[ct + (half * 4 + j) * 128] = h;
                         lo[ct + (half * 4 + j) * 128] = l;
                     }

@@ -80,7 +80,7 @@ struct Params {
                       // phase is what bounds those layers); ring sizes are multiples of it
     int epi_groups;  // 2 (the groups alternate tiles) or 1 (stride-2 depthwise front: shared memory goes to the boxes)
     long long* dbg;
-    int dbg_skip;  // debug instantiation only (YR_DWPW_SKIP): 1 = no depthwise math, 2 = no TMA box loads, 4 = no staging/phase 2 math
+    int dbg_skip;  // debug instantiation only (YR_DWPW_SKIP): 1 = no depthwise math, 2 = no TMA box loads, 4 = no staging / split / TMEM stores, 8 = no MMAs
 };
 constexpr int DW_TAIL_BYTES = 2048;  // per weight slot: 9 x 32 depthwise taps + 32 biases (1280 B), padded to 2 KB
 
@@ -356,10 +356,10 @@ __device__ __forceinline__ void converter_loop(const Params& p, const uint8_t* a
                         h[4 * j + 1] = __float_as_uint(hy);
                         h[4 * j + 2] = __float_as_uint(hz);
                         h[4 * j + 3] = __float_as_uint(hw);
-                        l[4 * j + 0] = __float_as_uint(tf32_rna(x.x - hx));
-                        l[4 * j + 1] = __float_as_uint(tf32_rna(x.y - hy));
-                        l[4 * j + 2] = __float_as_uint(tf32_rna(x.z - hz));
-                        l[4 * j + 3] = __float_as_uint(tf32_rna(x.w - hw));
+                        l[4 * j + 0] = __float_as_uint(tf32_lo(x.x, hx));
+                        l[4 * j + 1] = __float_as_uint(tf32_lo(x.y, hy));
+                        l[4 * j + 2] = __float_as_uint(tf32_lo(x.z, hz));
+                        l[4 * j + 3] = __float_as_uint(tf32_lo(x.w, hw));
                     }
                     tmem_st16(taddr + half * 16, h);
                     tmem_st16(taddr + 32 + half * 16, l);
@@ -432,11 +432,12 @@ __device__ __forceinline__ void dw_converter_loop(const Params& p, const uint8_t
                 // ---- phase 1: depthwise conv of this thread's patch ----
                 const float* sx = reinterpret_cast<const float*>(a_ring + (size_t)ra.slot * p.a_slot_bytes) + box_off;
                 const float4* wd = reinterpret_cast<const float4*>(b_ring + (size_t)bslot * p.b_slot_bytes + dw_off) + cq;
+                const float4 bv = wd[72];  // the accumulators start from the folded-BN bias (as in dw_tma_kernel)
                 float4 acc[PH][PW];
 #pragma unroll
                 for (int t = 0; t < PH; ++t)
 #pragma unroll
-                    for (int o = 0; o < PW; ++o) acc[t][o] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int o = 0; o < PW; ++o) acc[t][o] = bv;
                 if (worker && !(DBG && (p.dbg_skip & 1))) {
 #pragma unroll
                 for (int rr = 0; rr < IN_ROWS; ++rr) {
@@ -459,21 +460,21 @@ __device__ __forceinline__ void dw_converter_loop(const Params& p, const uint8_t
                     }
                 }
                 }
-                const float4 bv = wd[72];
                 // the staging tile is the head of this box's OWN slot: every warp of the group must be done reading the
                 // box before anyone overwrites it (no separate staging buffers: their 16 KB per group go to the A ring)
                 float* stage = reinterpret_cast<float*>(const_cast<uint8_t*>(a_ring) + (size_t)ra.slot * p.a_slot_bytes);
                 asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-                if (worker) {
+                const bool skip2 = DBG && (p.dbg_skip & 4);
+                if (worker && !skip2) {
 #pragma unroll
                 for (int t = 0; t < PH; ++t) {
 #pragma unroll
                     for (int o = 0; o < PW; ++o) {
                         float4 v;
-                        v.x = apply_act_rt(acc[t][o].x + bv.x, p.dw_act);
-                        v.y = apply_act_rt(acc[t][o].y + bv.y, p.dw_act);
-                        v.z = apply_act_rt(acc[t][o].z + bv.z, p.dw_act);
-                        v.w = apply_act_rt(acc[t][o].w + bv.w, p.dw_act);
+                        v.x = apply_act_rt(acc[t][o].x, p.dw_act);
+                        v.y = apply_act_rt(acc[t][o].y, p.dw_act);
+                        v.z = apply_act_rt(acc[t][o].z, p.dw_act);
+                        v.w = apply_act_rt(acc[t][o].w, p.dw_act);
                         const int r = (gy * PH + t) * p.TW + gx * PW + o;
                         *reinterpret_cast<float4*>(stage + r * BK + ((cq ^ (r & 7)) << 2)) = v;
                     }
@@ -482,7 +483,7 @@ __device__ __forceinline__ void dw_converter_loop(const Params& p, const uint8_t
                 asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                 // ---- phase 2: row gtid of the staging tile -> (hi, lo) TF32 columns of the TMEM stage ----
                 float4 v[8];
-                {
+                if (!skip2) {
                     const float* rowp = stage + gtid * BK;
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
@@ -496,6 +497,7 @@ __device__ __forceinline__ void dw_converter_loop(const Params& p, const uint8_t
                 tc_fence_after();
                 if (q == 0 && lane == 0) dbg_mark(p, 2, dq);
                 const uint32_t taddr = lane_base + rt.slot * (uint32_t)T_STAGE_COLS;
+                if (!skip2) {
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     uint32_t h[16], l[16];
@@ -507,13 +509,14 @@ __device__ __forceinline__ void dw_converter_loop(const Params& p, const uint8_t
                         h[4 * j + 1] = __float_as_uint(hy);
                         h[4 * j + 2] = __float_as_uint(hz);
                         h[4 * j + 3] = __float_as_uint(hw);
-                        l[4 * j + 0] = __float_as_uint(tf32_rna(x.x - hx));
-                        l[4 * j + 1] = __float_as_uint(tf32_rna(x.y - hy));
-                        l[4 * j + 2] = __float_as_uint(tf32_rna(x.z - hz));
-                        l[4 * j + 3] = __float_as_uint(tf32_rna(x.w - hw));
+                        l[4 * j + 0] = __float_as_uint(tf32_lo(x.x, hx));
+                        l[4 * j + 1] = __float_as_uint(tf32_lo(x.y, hy));
+                        l[4 * j + 2] = __float_as_uint(tf32_lo(x.z, hz));
+                        l[4 * j + 3] = __float_as_uint(tf32_lo(x.w, hw));
                     }
                     tmem_st16(taddr + half * 16, h);
                     tmem_st16(taddr + 32 + half * 16, l);
+                }
                 }
                 tmem_st_wait();
                 tc_fence_before();
@@ -746,7 +749,7 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
                 const uint32_t a_hi = tmem_base + (uint32_t)p.a_col0 + rt.slot * (uint32_t)T_STAGE_COLS;
                 const uint32_t a_lo = a_hi + 32u;
                 if (elect_one()) {
-                    for (int k8 = 0; k8 < ksteps; ++k8) {
+                    for (int k8 = 0; k8 < ((DBG && (p.dbg_skip & 8)) ? 0 : ksteps); ++k8) {
                         const uint64_t ko = (uint64_t)(k8 * 2);  // 32 bytes of K per step in the weight tile
                         const uint32_t ka = (uint32_t)(k8 * 8);  // 8 TMEM columns of K per step
                         if (CG == 2) {
@@ -777,8 +780,12 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
             if (++nt == p.n_tiles) nt = 0;
         }
         }
-    } else if (warp < 2 + NUM_CONVERTERS / 32) {
-        const int cw = warp - 2;
+    } else if (warp < 2 + NUM_CONVERTERS / 32 ||
+               (FRONT != 0 && p.conv_groups == 3 && warp >= 2 + NUM_CONVERTERS / 32 + 4 &&
+                warp < 2 + (NUM_CONVERTERS + NUM_EPILOGUE) / 32)) {
+        // converter warps; with three groups (depthwise front only, see Params::conv_groups) the second epilogue
+        // group's warps are the third one - through the SAME call site, so the loop exists once in the instruction cache
+        const int cw = warp < 2 + NUM_CONVERTERS / 32 ? warp - 2 : 8 + (warp & 3);
         if constexpr (FRONT != 0)
             dw_converter_loop<FRONT ? FRONT : 1, DBG>(p, gbase + a_off, gbase + b_off, tmem_base, bar0, item0, item1, warp & 3, lane,
                                                        cw >> 2);
@@ -788,12 +795,6 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
         // ===== epilogue =====
         const int ew8 = warp - (2 + NUM_CONVERTERS / 32);
         const int ew = ew8 & 3, eg = ew8 >> 2;
-        if constexpr (FRONT != 0) {
-            if (eg == 1 && p.conv_groups == 3) {  // third converter group (see Params::conv_groups)
-                dw_converter_loop<FRONT ? FRONT : 1, DBG>(p, gbase + a_off, gbase + b_off, tmem_base, bar0, item0, item1, warp & 3,
-                                                           lane, 2);
-            }
-        }
         float* stg = reinterpret_cast<float*>(gbase + epi_off + eg * p.epi_group_bytes) + ew * 32 * EPI_LD;
         float* s_bias = reinterpret_cast<float*>(gbase + epi_off + eg * p.epi_group_bytes + EPI_STAGE_BYTES);
         if (eg < p.epi_groups) {  // (a single-group launch leaves the second group's warps idle: it has no buffers)
@@ -1170,11 +1171,16 @@ int launch_dwpw(const yr_op& op, cudaStream_t s) {
     p.dbg = nullptr;
     p.dbg_skip = 0;
     static const bool debug = getenv("YR_PW_TC_DEBUG") != nullptr;  // developer aid only: timeline of CTA 0
+    // YR_PW_TC_DEBUG=2: the debug instantiation with its YR_DWPW_SKIP knobs but no timeline and no synchronisation,
+    // so that event timings around the launch stay valid
+    static const bool timeline = debug && atoi(getenv("YR_PW_TC_DEBUG")) != 2;
     if (debug) {
-        static long long* dbuf = nullptr;
-        if (!dbuf) cudaMalloc(&dbuf, 8 * ts::DBG_EV * sizeof(long long));
-        cudaMemsetAsync(dbuf, 0, 8 * ts::DBG_EV * sizeof(long long), s);
-        p.dbg = dbuf;
+        if (timeline) {
+            static long long* dbuf = nullptr;
+            if (!dbuf) cudaMalloc(&dbuf, 8 * ts::DBG_EV * sizeof(long long));
+            cudaMemsetAsync(dbuf, 0, 8 * ts::DBG_EV * sizeof(long long), s);
+            p.dbg = dbuf;
+        }
         const char* e = getenv("YR_DWPW_SKIP");
         p.dbg_skip = e ? atoi(e) : 0;
     }
@@ -1184,7 +1190,7 @@ int launch_dwpw(const yr_op& op, cudaStream_t s) {
         set_error("dwpw: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         return YR_ERR_CUDA;
     }
-    if (debug) {
+    if (timeline) {
         static long long h[8 * ts::DBG_EV];
         cudaStreamSynchronize(s);
         cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);

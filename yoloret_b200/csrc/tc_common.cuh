@@ -124,6 +124,13 @@ __host__ __device__ __forceinline__ float tf32_rna(float x) {
 #endif
 }
 
+// The low word of the 3xTF32 split of an ACTIVATION: x - hi is exact in fp32 and is handed to the tensor core as is.
+// kind::tf32 reads the top 19 bits of the 32-bit container and ignores the 13 low mantissa bits, so the operand is the
+// truncation of x - hi: error <= 2^-10 |lo| <= 2^-21 |x| (rounding it first, as the weight packers do at no cost,
+// would give 2^-22 |x|) against 2 integer-ALU instructions per element saved in every converter warp.  All three
+// tensor-core kernels use this one helper, so they stay bit-identical to each other.
+__device__ __forceinline__ float tf32_lo(float x, float hi) { return x - hi; }
+
 struct Ring {  // (slot, phase) cursor of a circular buffer; no div/mod on the hot path
     uint32_t slot = 0, phase = 0;
     __device__ __forceinline__ void advance(uint32_t n) {

@@ -64,6 +64,7 @@ class PostProcess:
         self._hdr, self._slots = hdr, slots
         self.host_flat = torch.zeros(self.flat.numel(), dtype=i32).pin_memory()
         self.host_flat2 = None  # second pinned landing buffer, allocated by streaming callers
+        self._snap = None       # device snapshots of the wire + side stream for enqueue_read
         self.image_shapes = torch.zeros(B, 2, dtype=f32, device=dev)
         self._shapes_host = None
         self.workspace_bytes = sum(t.numel() * t.element_size() for t in (
@@ -132,14 +133,31 @@ class PostProcess:
         return (self.flat.numel() if with_float_boxes else self.wire_words) * 4
 
     @_lib.on_device
-    def enqueue_read(self, slot: int = 0) -> torch.Tensor:
-        """Asynchronous device->host copy of the wire words on the current stream into pinned landing
-        buffer ``slot`` (0/1); the caller synchronises (event) before touching the returned tensor."""
+    def enqueue_read(self, slot: int = 0):
+        """Asynchronous read of the wire words into pinned landing buffer ``slot`` (0/1) that does NOT hold up the
+        compute stream: the current stream only snapshots the wire (device-to-device, a few microseconds), the
+        device->host copy runs on a side stream and overlaps the next step.  Returns ``(host tensor, event)``; the
+        caller synchronises the event before touching the tensor.  A slot may be reused once its event has fired."""
+        if self._snap is None:
+            self._snap = [torch.zeros(self.wire_words, dtype=torch.int32, device=self.device) for _ in range(2)]
+            self._read_stream = torch.cuda.Stream(self.device)
+            self._snapped = [torch.cuda.Event(), torch.cuda.Event()]
+            self._read_done = [torch.cuda.Event(), torch.cuda.Event()]
+            self._read_used = [False, False]
         if slot == 1 and self.host_flat2 is None:
             self.host_flat2 = torch.zeros(self.wire_words, dtype=torch.int32).pin_memory()
         dst = (self.host_flat if slot == 0 else self.host_flat2)[:self.wire_words]
-        dst.copy_(self.wire, non_blocking=True)
-        return dst
+        main = torch.cuda.current_stream(self.device)
+        if self._read_used[slot]:
+            main.wait_event(self._read_done[slot])  # the previous read out of this snapshot (two steps ago) is over
+        self._snap[slot].copy_(self.wire, non_blocking=True)
+        self._snapped[slot].record(main)
+        with torch.cuda.stream(self._read_stream):
+            self._read_stream.wait_event(self._snapped[slot])
+            dst.copy_(self._snap[slot], non_blocking=True)
+            self._read_done[slot].record(self._read_stream)
+        self._read_used[slot] = True
+        return dst, self._read_done[slot]
 
     @_lib.on_device
     def read_wire(self, with_float_boxes: bool = False) -> np.ndarray:

@@ -210,7 +210,8 @@ class YOLO(object):
         """Pipelined ``detect_batch`` over an iterable of host batches (pinned memory recommended; uint8 or float32):
         yields one result per batch, in order.  The host->device upload of batch i+1 runs on a copy stream into a
         second input slot while batch i computes, and each batch's detections come back with ONE
-        device->host copy, so in steady state a step costs max(compute, PCIe) instead of their sum.
+        device->host copy on a side stream (the compute stream only snapshots the wire buffer), so in steady state
+        a step costs max(compute, PCIe) instead of their sum.
         Every batch is still uploaded, computed and read back; nothing is cached between batches.
 
         Multi-GPU: pass ``gather`` (a ``parallel.DetectionGather`` over this engine's wire).  Every step then also
@@ -227,7 +228,7 @@ class YOLO(object):
         cs = self._copy_stream
         uploaded = [torch.cuda.Event(), torch.cuda.Event()]   # input slot filled
         consumed = [torch.cuda.Event(), torch.cuda.Event()]   # input slot free again (its graph finished)
-        landed = [torch.cuda.Event(), torch.cuda.Event()]     # wire copy of that step on the host
+        landed = [None, None]                                 # wire copy of that step on the host (side stream)
         kinds = [None, None]  # dtype flavour (uint8 / float32) of the batch sitting in each slot
 
         def upload(images, slot, first_use):
@@ -268,8 +269,7 @@ class YOLO(object):
             main.wait_event(uploaded[slot])
             self._graphs[(slot, kinds[slot])].replay()
             consumed[slot].record(main)
-            host = e.pp.enqueue_read(slot)
-            landed[slot].record(main)
+            host, landed[slot] = e.pp.enqueue_read(slot)
             ticket = gather.gather_async(read=gather_read) if gather is not None else None
             try:
                 nxt = next(it)
