@@ -72,7 +72,8 @@ struct Params {
     int up2, img_w;  // up2: every output row is stored to its 2x2 nearest-upsampled pixels (fused UpSampling2D)
     int nA, nT, nB, nAcc, resident, acc_stride, a_col0, items_per_cta, total_items, epi_group_bytes;
     uint32_t idesc;
-    uint32_t a_slot_bytes, b_slot_bytes;  // ring slot sizes (depthwise front: halo'd box / weight slot + dw taps)
+    uint32_t a_slot_bytes, b_slot_bytes;  // ring slot sizes (depthwise front: halo'd box + this k-block's dw taps / weight slot)
+    uint32_t a_taps_off;                  // depthwise front: byte offset of the taps + biases inside an activation slot
     // depthwise front: spatial tiling of the output (an item = one TH x TW tile of one image)
     int TH, TW, IW, tiles_h, tiles_w, Ho, Wo, pad_t, pad_l, dw_act;
     int conv_groups;  // converter groups taking k-blocks round-robin: 2, or 3 in the stride-1 depthwise front (the second
@@ -82,7 +83,9 @@ struct Params {
     long long* dbg;
     int dbg_skip;  // debug instantiation only (YR_DWPW_SKIP): 1 = no depthwise math, 2 = no TMA box loads, 4 = no staging / split / TMEM stores, 8 = no MMAs
 };
-constexpr int DW_TAIL_BYTES = 2048;  // per weight slot: 9 x 32 depthwise taps + 32 biases (1280 B), padded to 2 KB
+constexpr int DW_TAIL_BYTES = 2048;  // per slot of the packed image: 9 x 32 depthwise taps + 32 biases (1280 B), padded to 2 KB
+constexpr int DW_TAPS_BYTES = 1280;  // what of it is copied: it travels WITH THE BOX into the activation slot, so the
+                                     // converter groups never wait on the (shallow, MMA-paced) weight ring
 
 constexpr int BAR_A_FULL = 0;
 constexpr int BAR_A_EMPTY = BAR_A_FULL + MAX_A;
@@ -397,8 +400,8 @@ __device__ __forceinline__ void dw_converter_loop(const Params& p, const uint8_t
                                                   int grp) {
     constexpr int PH = 2, PW = 4, KS = 3;
     constexpr int IN_ROWS = (PH - 1) * S + KS, IN_COLS = (PW - 1) * S + KS;
-    Ring ra, rt, rb;
-    uint32_t dq = 0, b_seen = 0;
+    Ring ra, rt;
+    uint32_t dq = 0;
     const int gtid = q * 32 + lane;           // thread of the group; also the tile row / TMEM lane of phase 2
     const int cq = gtid & 7;                  // phase 1: channel quad (16-byte chunk of the pixel)
     const int pg = gtid >> 3;                 // phase 1: pixel patch
@@ -408,7 +411,6 @@ __device__ __forceinline__ void dw_converter_loop(const Params& p, const uint8_t
     const bool live_row = gtid < p.TH * p.TW;
     const int box_off = worker ? ((gy * PH * S) * p.IW + gx * PW * S) * BK + cq * 4 : 0;  // floats
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)p.a_col0;
-    const uint32_t dw_off = 2u * p.BN * 128u;
     const uint32_t bar_id = 3u + (uint32_t)grp;
     int turn = 0;  // dq % conv_groups
     for (int item = item0; item < item1; ++item) {
@@ -416,22 +418,11 @@ __device__ __forceinline__ void dw_converter_loop(const Params& p, const uint8_t
             const bool mine = turn == grp;
             if (++turn == p.conv_groups) turn = 0;
             if (mine) {
-                uint32_t bslot;
-                if (p.resident) {
-                    bslot = (uint32_t)kb;
-                    if (!((b_seen >> bslot) & 1u)) {
-                        mbar_wait(bar0 + 8u * (BAR_B_FULL + bslot), 0, 8);
-                        b_seen |= 1u << bslot;
-                    }
-                } else {
-                    bslot = rb.slot;
-                    mbar_wait(bar0 + 8u * (BAR_B_FULL + bslot), rb.phase, 8);
-                }
                 mbar_wait(bar0 + 8u * (BAR_A_FULL + ra.slot), ra.phase, 5);
                 if (q == 0 && lane == 0) dbg_mark(p, 1, dq);
                 // ---- phase 1: depthwise conv of this thread's patch ----
                 const float* sx = reinterpret_cast<const float*>(a_ring + (size_t)ra.slot * p.a_slot_bytes) + box_off;
-                const float4* wd = reinterpret_cast<const float4*>(b_ring + (size_t)bslot * p.b_slot_bytes + dw_off) + cq;
+                const float4* wd = reinterpret_cast<const float4*>(a_ring + (size_t)ra.slot * p.a_slot_bytes + p.a_taps_off) + cq;
                 const float4 bv = wd[72];  // the accumulators start from the folded-BN bias (as in dw_tma_kernel)
                 float4 acc[PH][PW];
 #pragma unroll
@@ -526,7 +517,6 @@ __device__ __forceinline__ void dw_converter_loop(const Params& p, const uint8_t
             }
             ra.advance(p.nA);
             rt.advance(p.nT);
-            if (!p.resident) rb.advance(p.nB);
         }
     }
 }
@@ -635,11 +625,16 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
                         ra.advance(p.nA);
                         continue;
                     }
-                    mbar_expect_tx(bar0 + 8u * (BAR_A_FULL + ra.slot), box_bytes);
-                    if constexpr (FRONT != 0)
+                    mbar_expect_tx(bar0 + 8u * (BAR_A_FULL + ra.slot), box_bytes + (FRONT != 0 ? (uint32_t)DW_TAPS_BYTES : 0u));
+                    if constexpr (FRONT != 0) {
                         tma_load_4d(base + a_off + ra.slot * p.a_slot_bytes, &tmA, bar0 + 8u * (BAR_A_FULL + ra.slot), kb * BK,
                                     bx, by, bimg);
-                    else
+                        // this k-block's depthwise taps + biases, from behind its weight tiles in the packed image
+                        bulk_load(base + a_off + ra.slot * p.a_slot_bytes + p.a_taps_off,
+                                  reinterpret_cast<const uint8_t*>(p.wp) + (size_t)kb * (2u * p.BN * 128u + DW_TAIL_BYTES) +
+                                      2u * p.BN * 128u,
+                                  DW_TAPS_BYTES, bar0 + 8u * (BAR_A_FULL + ra.slot));
+                    } else
                         tma_load_2d(base + a_off + ra.slot * p.a_slot_bytes, &tmA, bar0 + 8u * (BAR_A_FULL + ra.slot),
                                     kb * BK, (CG == 2 ? mt * 2 + (int)crank : mt) * BM);
                     dbg_mark(p, 0, dq++);
@@ -656,7 +651,8 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wp);
             // one weight slot of the packed image = [hi tile: BN rows x 128 B | lo tile].  CTA pair: this CTA keeps rows
             // [rank * BN/2, +BN/2) of both tiles: local slot = [hi half | lo half] (two bulk copies, one barrier)
-            const uint32_t g_slot = CG == 2 ? 2u * p.BN * 128u : b_slot_bytes;  // (depthwise front: + the taps behind the tiles)
+            const uint32_t g_slot = FRONT != 0 ? b_slot_bytes + DW_TAIL_BYTES   // (the taps behind the tiles go with the boxes)
+                                               : (CG == 2 ? 2u * p.BN * 128u : b_slot_bytes);
             const uint32_t half = p.BN * 64u;
             auto load_slot = [&](uint32_t slot, int src_slot) {
                 const uint32_t bar = bar0 + 8u * (BAR_B_FULL + slot);
@@ -1024,6 +1020,10 @@ static bool make_tiling_dw(int K, int N, int S, int Ho, int Wo, Tiling& t) {
         return e ? atoi(e) : 0;
     }();
     const int g_rule = t.KB >= 4 * ((t.BN + 31) / 32) ? 3 : 2;
+    static const int dw_min_nb = [] {  // experiment knob: fewest weight slots accepted beside a double-depth box ring
+        const char* e = getenv("YR_DWPW_MIN_NB");
+        return e ? atoi(e) : 2;
+    }();
     const int g_max = S == 1 ? (groups_knob == 2 || groups_knob == 3 ? groups_knob : g_rule) : 2;
     for (int i = 0; i < 9; ++i) {
         for (int G = g_max; G >= 2; --G) {
@@ -1032,8 +1032,8 @@ static bool make_tiling_dw(int K, int N, int S, int Ho, int Wo, Tiling& t) {
             c.TH = TH; c.TW = TW;
             c.IW = (TW - 1) * S + 3; c.IH = (TH - 1) * S + 3;
             if (c.IW > 256 || c.IH > 256 || (long long)c.IW * c.IH * 128 > DW_BOX_LIMIT) continue;
-            c.a_slot = (uint32_t)(((long long)c.IW * c.IH * 128 + 1023) / 1024 * 1024);
-            c.b_slot = 2u * c.BN * 128u + DW_TAIL_BYTES;
+            c.a_slot = (uint32_t)(((long long)c.IW * c.IH * 128 + DW_TAPS_BYTES + 1023) / 1024 * 1024);  // box + taps
+            c.b_slot = 2u * c.BN * 128u;
             c.conv_groups = G;
             // three converter groups borrow the second epilogue group's warps; stride 2: the boxes are ~4x the tile, so
             // one epilogue group gives its transpose buffers up
@@ -1048,11 +1048,13 @@ static bool make_tiling_dw(int K, int N, int S, int Ho, int Wo, Tiling& t) {
                 c.nB = c.KB;
             } else {
                 c.resident = 0;
-                long long nb = (avail - (long long)G * c.a_slot) / c.b_slot;
-                if (c.a_slot <= 32 * 1024 && (avail - 2ll * G * c.a_slot) / c.b_slot >= 2 * G) nb = (avail - 2ll * G * c.a_slot) / c.b_slot;
+                // Only the MMA issuer consumes the weight ring (the taps travel with the boxes), so its depth is free of
+                // the group count; two boxes per group (one being converted, one in flight) come first: a box takes
+                // ~3-5k cycles to land, a weight slot is needed once per k-block period and refills in ~2.5k.
+                long long nb = (avail - 2ll * G * c.a_slot) / c.b_slot;
+                if (c.a_slot > 32 * 1024 || nb < dw_min_nb) nb = (avail - (long long)G * c.a_slot) / c.b_slot;
                 if (nb > 6) nb = 6;
-                nb = nb / G * G;
-                if (nb < G) continue;
+                if (nb < 2) continue;
                 c.nB = (int)nb;
             }
             long long na = (avail - (long long)c.nB * c.b_slot) / c.a_slot;
@@ -1148,6 +1150,7 @@ int launch_dwpw(const yr_op& op, cudaStream_t s) {
     p.total_items = p.m_tiles;
     p.a_slot_bytes = t.a_slot;
     p.b_slot_bytes = t.b_slot;
+    p.a_taps_off = (uint32_t)((t.IW * t.IH * 128 + 127) / 128 * 128);
     p.TH = t.TH; p.TW = t.TW; p.IW = t.IW; p.tiles_h = t.tiles_h; p.tiles_w = t.tiles_w;
     p.Ho = op.Ho; p.Wo = op.Wo; p.pad_t = op.pad_t; p.pad_l = op.pad_l; p.dw_act = op.mode;
     p.epi_groups = t.epi_groups;
