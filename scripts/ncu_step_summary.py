@@ -3,6 +3,7 @@
 (2) profiles/<name>.json: per kernel kind the launch count, summed duration and DRAM traffic - the source of
 bench.py's `roofline.traffic`.   usage: ncu_step_summary.py raw.csv out_prefix batch"""
 import csv
+import re
 import json
 import sys
 
@@ -48,8 +49,11 @@ def main():
                           num(r[col["dram__bytes_write.sum"]]) * scale.get(units[col["dram__bytes_write.sum"]], 1.0)))
     for name, t, rd, wr in items:
         kind = next((k for pat, k in KIND if pat in name), "other")
-        if "pw_ts_kernel" in name and any(t in name for t in ("(int)1>", "(int)2>", ", 1>", ", 2>")):
-            kind = "dwpw"  # the depthwise-front instantiations of the tcgen05 pointwise kernel (YR_OP_DWPW)
+        m = re.search(r"pw_ts_kernel<([^>]*)>", name)
+        if m:
+            args = [a.replace("(bool)", "").replace("(int)", "").strip() for a in m.group(1).split(",")]
+            if len(args) >= 2 and args[1] not in ("0", "false"):  # <DBG, FRONT, CG>: FRONT = depthwise stride
+                kind = "dwpw"  # the depthwise-front instantiations of the tcgen05 pointwise kernel (YR_OP_DWPW)
         launches.append((name.split("(")[0], kind, t, rd, wr))
         k = kinds.setdefault(kind, {"launches": 0, "time_us": 0.0, "dram_bytes": 0.0})
         k["launches"] += 1

@@ -151,27 +151,9 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// waits of the leader on barriers that the peer CTA arrives on: cluster-scope acquire
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(0x989680u)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int what) {
-    for (uint32_t spins = 0; !mbar_try_wait_cluster(bar, parity); ++spins) {
-        if (spins > (1u << 12)) {
-            printf("yoloret_b200 pw_ts (CTA pair): mbarrier wait timed out (role %d, block %d, thread %d)\n", what, blockIdx.x,
-                   threadIdx.x);
-            __trap();
-        }
-    }
-}
+// waits of the leader on barriers that the peer CTA arrives on: the plain (CTA-scope) wait, as CUTLASS uses it for
+// cta_group::2 pipelines - the cluster-scope acquire form made the pair kernel 35 % slower
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int what) { mbar_wait(bar, parity, what); }
 __device__ __forceinline__ void umma_tf32_ts_2cta(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc,
                                                   uint32_t accumulate) {
     asm volatile(

@@ -34,13 +34,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps (and fails the launch loudly) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (and fails the launch loudly) instead of hanging the GPU.  The bound is wall time
+// (20 s on %globaltimer), not a spin count: under compute-sanitizer a legitimate wait can take millions of polls.
 static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int what) {
+    unsigned long long t0 = 0;
     for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
-        if (spins > (1u << 17)) {
-            printf("yoloret_b200 pw_tc: mbarrier wait timed out (role %d, block %d, thread %d)\n", what, blockIdx.x,
-                   threadIdx.x);
-            __trap();
+        if ((spins & 255u) == 255u) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 20000000000ull) {
+                printf("yoloret_b200 tcgen05 kernel: mbarrier wait timed out (role %d, block %d, thread %d)\n", what, blockIdx.x,
+                       threadIdx.x);
+                __trap();
+            }
         }
     }
 }
