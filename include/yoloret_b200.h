@@ -159,6 +159,11 @@ int yr_pw_ts2_supported(int K, int N); /* 1 when variant 4 (CTA pair) has a tili
 int64_t yr_dwpw_packed_floats(int K, int N);
 int yr_dwpw_pack(const float* w_pw, int K, int N, const float* w_dw, const float* b_dw, float* packed, void* stream);
 int yr_dwpw_supported(int C, int N, int stride, int Ho, int Wo);
+/* Host-only query of the plan the fused kernel would run (tests, diagnostics): plan[16] = {tile rows, tile cols, box
+ * rows, box cols, tiles per image (rows), (cols), converter groups, epilogue groups, box ring, TMEM stage ring, weight
+ * ring, accumulators, weights resident, n tile width, k-blocks, dynamic shared memory bytes}; returns 1 / 0 as
+ * yr_dwpw_supported. */
+int yr_dwpw_plan(int C, int N, int stride, int Ho, int Wo, int32_t* plan);
 
 /* ---- post-process: yolo_eval (reference code/yolo3/model.py:431-491) --------- */
 

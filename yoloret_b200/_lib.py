@@ -83,6 +83,7 @@ SYMBOLS = {
     "yr_dwpw_packed_floats": (C.c_int64, [C.c_int, C.c_int]),
     "yr_dwpw_pack": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "yr_dwpw_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "yr_dwpw_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]),
     "yr_decode_filter": (C.c_int, [C.POINTER(_P), _P, C.POINTER(YrDecodeParams), _P, _P, _P, _P, _P]),
     "yr_yolo_head": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int,
                                _P, _P, _P, _P, _P, _P]),

@@ -1002,6 +1002,10 @@ static bool make_tiling_dw(int K, int N, int S, int Ho, int Wo, Tiling& t) {
         return e ? atoi(e) : 0;
     }();
     const int g_rule = t.KB >= 4 * ((t.BN + 31) / 32) ? 3 : 2;
+    static const int dw_res_boxes = [] {  // experiment knob: 1 = resident weights even with one box per group
+        const char* e = getenv("YR_DWPW_RES_BOXES");
+        return e ? atoi(e) : 2;
+    }();
     static const int dw_min_nb = [] {  // experiment knob: fewest weight slots accepted beside a double-depth box ring
         const char* e = getenv("YR_DWPW_MIN_NB");
         return e ? atoi(e) : 2;
@@ -1025,7 +1029,12 @@ static bool make_tiling_dw(int K, int N, int S, int Ho, int Wo, Tiling& t) {
                                   // which then sees every mbarrier phase of it (see make_tiling on even rings)
             const long long fixed = 1024 + (long long)c.epi_groups * c.epi_group_bytes + BAR_BYTES;  // (staging tiles live in the A slots)
             const long long avail = SMEM_LIMIT - fixed;
-            if (c.KB <= MAX_B && (long long)c.KB * c.b_slot + (long long)G * c.a_slot <= avail) {
+            // resident weights only if they leave room for two boxes per group (small boxes): a group whose next box is
+            // requested only when it releases the current one waits the whole TMA latency (~3-5k cycles) every k-block
+            const int res_boxes = (c.a_slot <= 32 * 1024 && dw_res_boxes == 2) ? 2 * G : G;
+            const bool can_stream_deep = c.a_slot <= 32 * 1024 && (avail - 2ll * G * c.a_slot) / c.b_slot >= dw_min_nb;
+            if (c.KB <= MAX_B && ((long long)c.KB * c.b_slot + (long long)res_boxes * c.a_slot <= avail ||
+                                  (!can_stream_deep && (long long)c.KB * c.b_slot + (long long)G * c.a_slot <= avail))) {
                 c.resident = 1;
                 c.nB = c.KB;
             } else {
@@ -1401,4 +1410,17 @@ extern "C" int yr_dwpw_pack(const float* w_pw, int K, int N, const float* w_dw, 
 extern "C" int yr_dwpw_supported(int C, int N, int stride, int Ho, int Wo) {
     ts::Tiling t;
     return ts::make_tiling_dw(C, N, stride, Ho, Wo, t) ? 1 : 0;
+}
+
+/* The plan the fused kernel would run for this geometry (host-only query, no GPU needed): plan[16] = {tile rows, tile
+ * cols, box rows, box cols, tiles per image (rows), (cols), converter groups, epilogue groups, box ring, TMEM stage ring,
+ * weight ring, accumulators, weights resident, n tile width, k-blocks, dynamic shared memory in bytes}.  1 / 0 as
+ * yr_dwpw_supported. */
+extern "C" int yr_dwpw_plan(int C, int N, int stride, int Ho, int Wo, int32_t* plan) {
+    ts::Tiling t;
+    if (!plan || !ts::make_tiling_dw(C, N, stride, Ho, Wo, t)) return 0;
+    const int v[16] = {t.TH, t.TW, t.IH, t.IW, t.tiles_h, t.tiles_w, t.conv_groups, t.epi_groups, t.nA, t.nT, t.nB, t.nAcc,
+                       t.resident, t.BN, t.KB, (int)t.smem};
+    for (int i = 0; i < 16; ++i) plan[i] = v[i];
+    return 1;
 }
