@@ -79,7 +79,9 @@ struct Params {
     int conv_groups;  // converter groups taking k-blocks round-robin: 2, or 3 in the stride-1 depthwise front (the second
                       // epilogue group's warps convert instead: narrow outputs leave the epilogue idle, the depthwise
                       // phase is what bounds those layers); ring sizes are multiples of it
-    int epi_groups;  // 2 (the groups alternate tiles) or 1 (stride-2 depthwise front: shared memory goes to the boxes)
+    int epi_groups;  // 2 or 1 (stride-2 depthwise front / three converter groups: the second group's resources go elsewhere)
+    int epi_split;   // two groups: 1 = both drain EVERY tile, alternating its 32-column chunks (balanced for any tile count:
+                     // the few tiles a CTA gets on the small layers rarely split evenly); 0 = the groups alternate tiles
     long long* dbg;
     int dbg_skip;  // debug instantiation only (YR_DWPW_SKIP): 1 = no depthwise math, 2 = no TMA box loads, 4 = no staging / split / TMEM stores, 8 = no MMAs
 };
@@ -189,7 +191,9 @@ __device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, const
     Ring racc;
     int mt = item0 / p.n_tiles, nt = item0 - mt * p.n_tiles;
     for (int item = item0; item < item1; ++item, ++it) {
-        if (p.epi_groups == 1 ? grp == 0 : (int)(it & 1u) == grp) {
+        const bool split = p.epi_groups == 2 && p.epi_split != 0;
+        if (split || (p.epi_groups == 1 ? grp == 0 : (int)(it & 1u) == grp)) {
+            const int cstep = split ? 64 : 32;
             const uint32_t acc = racc.slot;
             const int row0 = (CG == 2 ? mt * 2 + (int)crank : mt) * BM + q * 32;
             const int ncols = min(p.BN, p.N - nt * p.BN);
@@ -210,7 +214,7 @@ __device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, const
             const uint32_t tsrc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.acc_stride;
             bool waited = false;
             float v[32];
-            for (int c0 = 0; c0 < ncols; c0 += 32) {
+            for (int c0 = split ? grp * 32 : 0; c0 < ncols; c0 += cstep) {
                 const int c = c0 + sub_c;
                 const int n = nt * p.BN + c;
                 const bool col_ok = c < ncols;
@@ -241,7 +245,7 @@ __device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, const
                     *reinterpret_cast<float4*>(stg + lane * EPI_LD + 4 * j) =
                         make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 // v now lives in shared memory: fetch the next chunk into the same registers while this one is stored
-                if (!HAS_RES && c0 + 32 < ncols) tmem_ld32_issue(tsrc + c0 + 32, v);
+                if (!HAS_RES && c0 + cstep < ncols) tmem_ld32_issue(tsrc + c0 + cstep, v);
                 __syncwarp();
                 if (col_ok) {
                     const float4 bv = *reinterpret_cast<const float4*>(s_bias + n);
@@ -547,7 +551,7 @@ pw_ts_kernel(const __grid_constant__ CUtensorMap tmA, const Params p) {
         }
         for (int s = 0; s < p.nAcc; ++s) {
             mbar_init(bar0 + 8u * (BAR_ACC_FULL + s), 1);
-            mbar_init(bar0 + 8u * (BAR_ACC_EMPTY + s), 128 * CG);
+            mbar_init(bar0 + 8u * (BAR_ACC_EMPTY + s), 128 * CG * ((p.epi_groups == 2 && p.epi_split) ? 2 : 1));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1072,6 +1076,23 @@ static bool make_tiling_dw(int K, int N, int S, int Ho, int Wo, Tiling& t) {
 
 }  // namespace ts
 
+// Two epilogue groups can share the work two ways: alternate TILES (balanced when a CTA drains many tiles) or alternate
+// the 32-column CHUNKS of every tile (balanced for any tile count, but 2:1 on a 96-column tile).  Pick the smaller
+// makespan in columns; measured on B200: 26x26 48->288 (5 tiles per CTA) 24.5 -> 22.5 us, 13x13 120->720 (3 tiles)
+// 24.5 -> 22.5 us with chunks; 208x208 24->96 fused (146 tiles of 3 chunks) 258 -> 309 us, so that one keeps tiles.
+static int choose_epi_split(int items_per_cta, int ncols) {
+    static const int knob = [] {  // experiment knob: YR_PW_EPI_SPLIT=0 / 1 force tiles / chunks
+        const char* e = getenv("YR_PW_EPI_SPLIT");
+        return e ? atoi(e) : -1;
+    }();
+    if (knob == 0 || knob == 1) return knob;
+    long long g0 = 0, g1 = 0;
+    for (int c = 0; c < ncols; c += 32) ((c >> 5) & 1 ? g1 : g0) += (ncols - c < 32 ? ncols - c : 32);
+    const long long by_chunks = (long long)items_per_cta * (g0 > g1 ? g0 : g1);
+    const long long by_tiles = (long long)((items_per_cta + 1) / 2) * ncols;
+    return by_chunks < by_tiles ? 1 : 0;
+}
+
 // Fused depthwise 3x3 (+BN +act) -> pointwise 1x1 (+BN +act +residual): YR_OP_DWPW.
 int launch_dwpw(const yr_op& op, cudaStream_t s) {
     YR_CHECK_ARG(op.in && op.out && op.w_tc && op.bias, "dwpw: null pointer (w_tc = yr_dwpw_pack output)");
@@ -1145,6 +1166,7 @@ int launch_dwpw(const yr_op& op, cudaStream_t s) {
     p.TH = t.TH; p.TW = t.TW; p.IW = t.IW; p.tiles_h = t.tiles_h; p.tiles_w = t.tiles_w;
     p.Ho = op.Ho; p.Wo = op.Wo; p.pad_t = op.pad_t; p.pad_l = op.pad_l; p.dw_act = op.mode;
     p.epi_groups = t.epi_groups;
+    p.epi_split = 0;  // set with items_per_cta below
     p.conv_groups = t.conv_groups;
     static DeviceOnce attr_once;  // function attributes are per device
     bool& attr_set = attr_once.cur();
@@ -1160,6 +1182,7 @@ int launch_dwpw(const yr_op& op, cudaStream_t s) {
     }
     const int max_ctas = tc::num_sms();
     p.items_per_cta = (p.total_items + max_ctas - 1) / max_ctas;
+    p.epi_split = p.epi_groups == 2 ? choose_epi_split(p.items_per_cta, p.BN < p.N ? p.BN : p.N) : 0;
     const int grid = (p.total_items + p.items_per_cta - 1) / p.items_per_cta;
     p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(t.BN >> 3) << 17) | ((uint32_t)(ts::BM >> 4) << 24);
     p.dbg = nullptr;
@@ -1273,6 +1296,7 @@ static int launch_pw_ts_cg(const yr_op& op, cudaStream_t s) {
     p.TH = p.TW = p.IW = p.tiles_h = p.tiles_w = 1;
     p.Ho = p.Wo = p.pad_t = p.pad_l = p.dw_act = 0;
     p.epi_groups = CG == 2 ? t.epi_groups : 2;
+    p.epi_split = 0;  // set with items_per_cta below
     p.conv_groups = 2;
     static DeviceOnce attr_once;  // function attributes are per device
     bool& attr_set = attr_once.cur();
@@ -1291,6 +1315,7 @@ static int launch_pw_ts_cg(const yr_op& op, cudaStream_t s) {
     // L2 either way), and the split is item- not block-granular, which fills more SMs when there are few row blocks
     // (26x26 x 64 images = 338 blocks x 2 n tiles: 136 CTAs x 5 items instead of 113 x 6)
     p.items_per_cta = (p.total_items + max_ctas - 1) / max_ctas;
+    p.epi_split = p.epi_groups == 2 ? choose_epi_split(p.items_per_cta, p.BN < p.N ? p.BN : p.N) : 0;
     const int grid = CG * ((p.total_items + p.items_per_cta - 1) / p.items_per_cta);
     p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(t.BN >> 3) << 17) | ((uint32_t)((CG * ts::BM) >> 4) << 24);
     p.dbg = nullptr;
