@@ -109,7 +109,12 @@ typedef struct yr_op {
     int32_t Ho, Wo, N;       /* output height / width / channels */
     int32_t k, stride, pad_t, pad_l;
     int32_t ld_in, ld_in2, ld_in3, ld_in4, ld_out, ld_res;
-    int32_t K2, K3, K4;      /* RFCR: channels of in2..in4 */
+    int32_t K2, K3, K4;      /* RFCR: channels of in2..in4.
+                                PW (variant 3 / 4), stacked outputs: two 1x1 convs that read the SAME tensor (reference
+                                code/yolo3/model.py:296-305: the y conv and the next bottom-up conv of a head stage) run as one
+                                GEMM over [W1 | W2]: K2 > 0 = the first conv's (padded) column count - columns [0, K2) go to
+                                `out` (row stride ld_out), columns [K2, N) to `aux` (row stride ld_in2), K2 % 4 == 0; K3 != 0 =
+                                the first conv is linear (no activation) while `act` applies to the second */
     int32_t variant;         /* PW kernel choice: 0 = auto (tcgen05 when w_tc is given), 1 = SIMT fp32,
                                 2 = tcgen05 3xTF32, A and B operands in shared memory (w_tc = yr_pw_tc_pack image),
                                 3 = tcgen05 3xTF32, A operand in tensor memory (w_tc = yr_pw_ts_pack image),
@@ -125,7 +130,7 @@ typedef struct yr_op {
     const float* res;
     const float* scale;
     const float* w_tc;       /* PW: weight image made by yr_pw_tc_pack (variant 0/2) or yr_pw_ts_pack (variant 3), or NULL */
-    float* aux;              /* DW: squeeze-excite partial sums (see above), or NULL */
+    float* aux;              /* DW: squeeze-excite partial sums (see above), or NULL; PW with K2 > 0: the second output */
 } yr_op;
 
 /* Library identity / errors. */

@@ -8,7 +8,7 @@ pytestmark = pytest.mark.gpu
 
 from yoloret_b200 import _lib  # noqa: E402
 from yoloret_b200._lib import YrOp  # noqa: E402
-from ophelp import run_op, act_ref, pw_op, ACT  # noqa: E402
+from ophelp import run_op, act_ref, pw_op, pack_tc, ACT  # noqa: E402
 
 RTOL, ATOL = 2e-5, 2e-5  # fp32 kernels vs an fp64 reference of the same op
 
@@ -98,6 +98,51 @@ def test_pw_fused_upsampling(built_lib, variant, B, H, W, K, N, act):
     assert fused.shape == (B, 2 * H, 2 * W, N + 16)
     assert torch.equal(fused[..., :N], want)
     assert torch.isnan(fused[..., N:]).all()
+
+
+@pytest.mark.parametrize("variant", [3, 4])
+@pytest.mark.parametrize("B,H,W,K,N1,N2,act2,gate", [
+    (8, 52, 52, 128, 256, 128, "relu6", True),    # conv2d_23*{conv2d_24 (y3, linear), conv2d_25} of the benchmarked net
+    (16, 26, 26, 256, 256, 256, "relu6", True),   # conv2d_29*{conv2d_30 (y2), conv2d_31}
+    (3, 13, 13, 72, 24, 40, "swish", False),      # split inside an n tile and inside a 32-column chunk (24 % 32 != 0)
+    (2, 9, 7, 48, 200, 120, "none", False),       # split in the second n tile (N = 320: two tiles of 160)
+    (1, 6, 8, 256, 256, 256, "relu6", True),      # 48 rows: one partial row block (a CTA pair's second block is empty)
+    (2, 12, 16, 128, 256, 128, "relu6", True),    # three row blocks: an odd number for the pair kernel
+    (7, 6, 8, 256, 256, 256, "relu6", True),
+])
+def test_pw_stacked_outputs(built_lib, variant, B, H, W, K, N1, N2, act2, gate):
+    """Two 1x1 convs that read the same tensor (reference code/yolo3/model.py:296-305: a head stage's y conv and the next
+    bottom-up conv) as ONE GEMM over [W1 | W2] with two destinations: every output bit equals the two separate ops
+    (a column's accumulation does not depend on its neighbours), the first block stays linear, and nothing is written
+    outside either channel slice."""
+    a = _rand(B, H, W, K, seed=41).cuda()
+    w1 = _rand(K, N1, seed=42, scale=K ** -0.5).cuda()
+    w2 = _rand(K, N2, seed=43, scale=K ** -0.5).cuda()
+    b1, b2 = _rand(N1, seed=44).cuda(), _rand(N2, seed=45).cuda()
+    scale = torch.rand(B, K, generator=torch.Generator().manual_seed(46)).cuda() if gate else None
+    sep1 = pw_op(a, w1, b1, "none", None, scale, variant=variant)
+    sep2 = pw_op(a, w2, b2, act2, None, scale, variant=variant)
+    w = torch.cat([w1, w2], 1).contiguous()
+    bias = torch.cat([b1, b2]).contiguous()
+    out1 = torch.full((B, H, W, N1 + 8), float("nan"), device="cuda")
+    out2 = torch.full((B, H, W, N2 + 16), float("nan"), device="cuda")
+    op = YrOp()
+    op.kind, op.act, op.variant = _lib.OP_PW, ACT[act2], variant
+    op.B, op.H, op.W, op.C, op.Ho, op.Wo, op.N = B, H, W, K, H, W, N1 + N2
+    op.ld_in, op.ld_out, op.ld_in2, op.K2, op.K3 = K, N1 + 8, N2 + 16, N1, 1
+    op.in_, op.out, op.aux = a.data_ptr(), out1.data_ptr(), out2.data_ptr()
+    op.w, op.bias = w.data_ptr(), bias.data_ptr()
+    if gate:
+        op.scale = scale.data_ptr()
+    packed = pack_tc(w, variant)
+    op.w_tc = packed.data_ptr()
+    run_op(op)
+    assert torch.equal(out1[..., :N1], sep1), float((out1[..., :N1] - sep1).abs().max())
+    assert torch.equal(out2[..., :N2], sep2), float((out2[..., :N2] - sep2).abs().max())
+    assert torch.isnan(out1[..., N1:]).all() and torch.isnan(out2[..., N2:]).all()
+    bad = YrOp.from_buffer_copy(op)
+    bad.variant = 2                                   # the shared-memory-A kernel has no second destination
+    assert _lib.lib().yr_run_ops((YrOp * 1)(bad), 1, torch.cuda.current_stream().cuda_stream) < 0
 
 
 @pytest.mark.parametrize("variant", [2, 3, 4])

@@ -86,6 +86,10 @@ extern "C" int yr_run_ops(const yr_op* ops, int n_ops, void* stream) {
         switch (op.kind) {
             case YR_OP_STEM: rc = launch_stem(op, s); break;
             case YR_OP_PW:
+                if (op.K2 != 0 && op.variant != 3 && op.variant != 4) {
+                    set_error("run_ops: op %d: stacked outputs (K2 = %d) need the tensor-memory-A kernel (variant 3 or 4)", i, op.K2);
+                    return YR_ERR_INVALID;
+                }
                 if (op.variant == 4) rc = launch_pw_ts2(op, s);
                 else if (op.variant == 3) rc = launch_pw_ts(op, s);
                 else rc = (op.variant == 2 || (op.variant == 0 && op.w_tc != nullptr)) ? launch_pw_tc(op, s) : launch_pw(op, s);

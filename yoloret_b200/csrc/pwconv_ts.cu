@@ -80,6 +80,8 @@ struct Params {
                       // epilogue group's warps convert instead: narrow outputs leave the epilogue idle, the depthwise
                       // phase is what bounds those layers); ring sizes are multiples of it
     int epi_groups;  // 2 or 1 (stride-2 depthwise front / three converter groups: the second group's resources go elsewhere)
+    float* out2;     // stacked outputs (yr_op.aux): columns >= n_split go to out2 (row stride ld_out2), re-based to 0
+    int ld_out2, n_split, first_linear;  // first_linear: columns < n_split skip the activation
     int epi_split;   // two groups: 1 = both drain EVERY tile, alternating its 32-column chunks (balanced for any tile count:
                      // the few tiles a CTA gets on the small layers rarely split evenly); 0 = the groups alternate tiles
     long long* dbg;
@@ -249,17 +251,34 @@ __device__ __forceinline__ void epilogue_loop(const Params& p, float* stg, const
                 __syncwarp();
                 if (col_ok) {
                     const float4 bv = *reinterpret_cast<const float4*>(s_bias + n);
-                    float* op = p.out + (size_t)(row0 + sub_r) * p.ld_out + n;
+                    // stacked outputs: two 1x1 convs that read the same tensor run as ONE GEMM over [W1 | W2]; this
+                    // lane's four columns belong to one of them (n_split % 4 == 0)
+                    const bool second = !SP && !UP2 && p.n_split > 0 && n >= p.n_split;
+                    const bool linear = !SP && !UP2 && p.n_split > 0 && !second && p.first_linear != 0;
+                    const int ldo = second ? p.ld_out2 : p.ld_out;
+                    float* op = (second ? p.out2 + (n - p.n_split) : p.out + n) + (size_t)(row0 + sub_r) * ldo;
                     const float* sp = stg + sub_r * EPI_LD + sub_c;
-                    const size_t ostep = (size_t)4 * p.ld_out;
+                    const size_t ostep = (size_t)4 * ldo;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         if (SP ? (pix[i] >= 0) : (sub_r + 4 * i < rows)) {
                             float4 x = *reinterpret_cast<const float4*>(sp + (4 * i) * EPI_LD);
-                            x.x = apply_act<ACT>(x.x + bv.x);
-                            x.y = apply_act<ACT>(x.y + bv.y);
-                            x.z = apply_act<ACT>(x.z + bv.z);
-                            x.w = apply_act<ACT>(x.w + bv.w);
+                            if (HAS_RES || SP || UP2) {
+                                // (kept in this exact form: the compiler contracts the activation's last multiply with
+                                // the residual add into one FMA, and every instantiation must round the same way)
+                                x.x = apply_act<ACT>(x.x + bv.x);
+                                x.y = apply_act<ACT>(x.y + bv.y);
+                                x.z = apply_act<ACT>(x.z + bv.z);
+                                x.w = apply_act<ACT>(x.w + bv.w);
+                            } else {  // (stacked outputs never carry a residual: checked by the launcher)
+                                x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
+                                if (!linear) {
+                                    x.x = apply_act<ACT>(x.x);
+                                    x.y = apply_act<ACT>(x.y);
+                                    x.z = apply_act<ACT>(x.z);
+                                    x.w = apply_act<ACT>(x.w);
+                                }
+                            }
                             if (HAS_RES) { x.x += rv[i].x; x.y += rv[i].y; x.z += rv[i].z; x.w += rv[i].w; }
                             if (SP) {
                                 st4(p.out + (size_t)pix[i] * p.ld_out + n, x);
@@ -1163,6 +1182,7 @@ int launch_dwpw(const yr_op& op, cudaStream_t s) {
     p.a_slot_bytes = t.a_slot;
     p.b_slot_bytes = t.b_slot;
     p.a_taps_off = (uint32_t)((t.IW * t.IH * 128 + 127) / 128 * 128);
+    p.out2 = nullptr; p.ld_out2 = 0; p.n_split = 0; p.first_linear = 0;
     p.TH = t.TH; p.TW = t.TW; p.IW = t.IW; p.tiles_h = t.tiles_h; p.tiles_w = t.tiles_w;
     p.Ho = op.Ho; p.Wo = op.Wo; p.pad_t = op.pad_t; p.pad_l = op.pad_l; p.dw_act = op.mode;
     p.epi_groups = t.epi_groups;
@@ -1231,11 +1251,16 @@ static int launch_pw_ts_cg(const yr_op& op, cudaStream_t s) {
     YR_CHECK_ARG(op.in && op.out && op.w_tc && op.bias, "pw_ts: null pointer (w_tc = yr_pw_ts_pack output)");
     YR_CHECK_ARG(op.C > 0 && op.C % 8 == 0 && op.N > 0 && op.N % 8 == 0, "pw_ts: K=%d N=%d must be multiples of 8", op.C,
                  op.N);
-    YR_CHECK_ARG(op.ld_in >= op.C && op.ld_in % 4 == 0 && op.ld_out >= op.N && op.ld_out % 4 == 0,
+    const int n_first = op.K2 > 0 ? op.K2 : op.N;  // stacked outputs: columns [0, K2) -> out, [K2, N) -> aux
+    YR_CHECK_ARG(op.ld_in >= op.C && op.ld_in % 4 == 0 && op.ld_out >= n_first && op.ld_out % 4 == 0,
                  "pw_ts: bad ld_in=%d ld_out=%d", op.ld_in, op.ld_out);
     YR_CHECK_ARG(!op.res || (op.ld_res >= op.N && op.ld_res % 4 == 0), "pw_ts: bad ld_res=%d", op.ld_res);
     YR_CHECK_ARG(((uintptr_t)op.in | (uintptr_t)op.out | (uintptr_t)op.w_tc | (uintptr_t)op.bias | (uintptr_t)op.res |
                   (uintptr_t)op.scale) % 16 == 0, "pw_ts: pointers must be 16-byte aligned");
+    YR_CHECK_ARG(op.K2 == 0 || (op.K2 > 0 && op.K2 < op.N && op.K2 % 4 == 0 && op.aux && (uintptr_t)op.aux % 16 == 0 &&
+                                op.ld_in2 >= op.N - op.K2 && op.ld_in2 % 4 == 0 && !op.res && op.Ho == op.H && op.Wo == op.W),
+                 "pw_ts: stacked outputs need 0 < K2 < N, K2 %% 4 == 0, aux (second output, 16-byte aligned), ld_in2 >= N - K2, "
+                 "no residual and no fused upsampling (K2=%d N=%d ld_in2=%d)", op.K2, op.N, op.ld_in2);
     const long long M = (long long)op.B * op.H * op.W;
     YR_CHECK_ARG(M > 0 && M < (1ll << 31) - 256, "pw_ts: bad row count");
     YR_CHECK_ARG((op.Ho == op.H && op.Wo == op.W) || (op.Ho == 2 * op.H && op.Wo == 2 * op.W && !op.res),
@@ -1269,6 +1294,10 @@ static int launch_pw_ts_cg(const yr_op& op, cudaStream_t s) {
     p.res = op.res;
     p.scale = op.scale;
     p.out = (float*)op.out;
+    p.out2 = op.K2 > 0 ? op.aux : nullptr;
+    p.ld_out2 = op.ld_in2;
+    p.n_split = op.K2 > 0 ? op.K2 : 0;
+    p.first_linear = op.K3;
     p.M = (int)M;
     p.K = op.C;
     p.N = op.N;

@@ -62,7 +62,7 @@ class Engine:
                  num_scales: int = 3, max_boxes: int = 20, cand_cap: Optional[int] = None,
                  device: Optional[torch.device] = None, pw_variant: int = _lib.PW_AUTO, input_u8: bool = False,
                  fuse_se: bool = True, lanes: int = 1, autotune: bool = True, fuse_up2: bool = True,
-                 num_anchors: int = 3, fuse_dwpw: bool = True, fold_linear: bool = True):
+                 num_anchors: int = 3, fuse_dwpw: bool = True, fold_linear: bool = True, stack_pw: bool = True):
         if not torch.cuda.is_available():
             raise _lib.YrError("yoloret_b200.Engine needs a CUDA device (no CPU fallback exists)")
         self.lib = _lib.lib()
@@ -74,10 +74,11 @@ class Engine:
         with torch.cuda.device(self.device):  # allocations, attribute caches and the autotuner run on that GPU
             self._init(model_name, num_classes, input_hw, batch, weights, anchors, micro_batch, num_scales, max_boxes,
                        cand_cap, pw_variant, input_u8, fuse_se, lanes, autotune, fuse_up2, num_anchors, fuse_dwpw,
-                       fold_linear)
+                       fold_linear, stack_pw)
 
     def _init(self, model_name, num_classes, input_hw, batch, weights, anchors, micro_batch, num_scales, max_boxes,
-              cand_cap, pw_variant, input_u8, fuse_se, lanes, autotune, fuse_up2, num_anchors, fuse_dwpw=True, fold_linear=True):
+              cand_cap, pw_variant, input_u8, fuse_se, lanes, autotune, fuse_up2, num_anchors, fuse_dwpw=True, fold_linear=True,
+              stack_pw=True):
         # the reference derives anchors per scale as num_anchors // num_scales (code/yolo.py:214-216); decode, the head
         # width and the y_true layout of this engine are written for 3 per scale (every shipped anchor file: 9 / 3)
         if int(num_anchors) != 3:
@@ -106,6 +107,7 @@ class Engine:
         self.autotune = bool(autotune)
         self.fuse_up2 = bool(fuse_up2)
         self.fuse_dwpw = bool(fuse_dwpw)
+        self.stack_pw = bool(stack_pw)
         self.cand_cap_arg = cand_cap
         self._check_weights(weights)
         self._alloc()
@@ -216,6 +218,7 @@ class Engine:
                 mat = _pad_cols(np.concatenate(mats, 0), L.out.C)
                 self.wdev[i] = (self._dev(mat), self._dev(w["weighted_sum/alpha"]))
         self._find_dwpw_pairs()
+        self._find_stacked_pw()
         torch.cuda.synchronize(self.device)
         self.weight_bytes = sum(a.numel() * 4 + b.numel() * 4 for a, b in self.wdev.values())
 
@@ -261,6 +264,45 @@ class Engine:
             _lib.check(self.lib.yr_dwpw_pack(wp.data_ptr(), C_, N_, wd.data_ptr(), bd.data_ptr(), blob.data_ptr(),
                                              self._stream()), "yr_dwpw_pack")
             self.dwpw_blob[i] = blob
+
+    def _find_stacked_pw(self):
+        """Two consecutive 1x1 convs that read the SAME tensor through the same SE gate - after the linear folding that is
+        a head stage's y conv and the next bottom-up conv (reference code/yolo3/model.py:296-305, here
+        conv2d_23*conv2d_24 | conv2d_23*conv2d_25 and conv2d_29*conv2d_30 | conv2d_29*conv2d_31) - run as ONE GEMM over
+        [W1 | W2] with two destinations (yr_op.K2 / aux): the shared input is read, gated and split into TF32 once.
+        Bit-identical to the two ops (tests/test_gpu_ops.py::test_pw_stacked_outputs).  Needs the tensor-memory-A
+        kernel; with the autotuner on, a pair stays stacked only if that measures faster than its two ops."""
+        self.pw_stack: Dict[int, Dict] = {}
+        if not self.stack_pw or self.pw_variant not in (_lib.PW_AUTO, _lib.PW_TS, _lib.PW_TS2):
+            return
+        Ls = self.net.layers
+        taken = set()
+        for i in range(len(Ls) - 1):
+            a, b = Ls[i], Ls[i + 1]
+            if i in taken or a.kind != "pw" or b.kind != "pw" or (i - 1) in self.dwpw_blob:
+                continue
+            va, vb = a.inp[0], b.inp[0]
+            if not (va.buf is vb.buf and va.off == vb.off and va.C == vb.C and a.gate is b.gate):
+                continue
+            if a.res is not None or b.res is not None or self._up2_fused_into(i) or self._up2_fused_into(i + 1):
+                continue
+            if a.act != "none" and a.act != b.act:
+                continue
+            if self.wts.get(i) is None or self.wts.get(i + 1) is None:
+                continue
+            w = torch.cat([self.wdev[i][0], self.wdev[i + 1][0]], 1).contiguous()
+            bias = torch.cat([self.wdev[i][1], self.wdev[i + 1][1]]).contiguous()
+            n1 = int(self.wdev[i][0].shape[1])
+            if n1 % 4 or int(self.lib.yr_pw_ts_packed_floats(int(w.shape[0]), int(w.shape[1]))) <= 0:
+                continue
+            img = self._pack_tc(w, _lib.PW_TS)
+            if img is None:
+                continue
+            pair_ok = bool(self.lib.yr_pw_ts2_supported(int(w.shape[0]), int(w.shape[1])))
+            variant = _lib.PW_TS2 if (self.pw_variant == _lib.PW_TS2 and pair_ok) else _lib.PW_TS
+            self.pw_stack[i] = {"w": w, "bias": bias, "img": img, "n1": n1, "variant": variant, "pair_ok": pair_ok,
+                                "first_linear": 1 if (a.act == "none" and b.act != "none") else 0}
+            taken.add(i + 1)
 
     def _pack_tc(self, w_kn: torch.Tensor, variant: int) -> Optional[torch.Tensor]:
         """yr_pw_tc_pack / yr_pw_ts_pack: [K,N] fp32 -> split/swizzled TF32 (hi, lo) image for a tcgen05 kernel."""
@@ -319,10 +361,14 @@ class Engine:
         if not both:
             return
         nb = min(self.micro, self.batch)
+        stack_cands, self.pw_stack = self.pw_stack, {}   # time the layers one by one first, then the stacked pairs
+        self._plans.clear()
         ops, cnt = self.build_plan(0, nb)
         op_of = {li: k for k, (_kind, _name, _b, _f, li) in enumerate(self._plan_meta)}
         st = self._stream()
         cache: Dict[Tuple, int] = {}
+        best_ms: Dict[int, float] = {}
+        tcache: Dict[Tuple, float] = {}
         self.autotune_log: List[Tuple] = []
         for i in both:
             if i not in op_of:
@@ -351,9 +397,43 @@ class Engine:
                 # run-to-run noise does not flip the picks (outputs are bit-identical either way)
                 best = min(t, key=lambda v: t[v])
                 cache[key] = best if t[best] < 0.98 * t[_lib.PW_TS] else _lib.PW_TS
+                tcache[key] = t[cache[key]]
                 self.autotune_log.append((L.name, key[:4]) + tuple(round(t.get(v, 0.0) * 1e3, 1)
                                                                     for v in (_lib.PW_TC, _lib.PW_TS, _lib.PW_TS2)))
             self.pw_choice[i] = cache[key]
+            best_ms[i] = tcache[key]
+        # stacked pairs ([W1 | W2] as one GEMM): keep one only if it beats its two ops by more than the noise
+        self.stack_log: List[Tuple] = []
+        for i, cand in stack_cands.items():
+            if i not in best_ms or (i + 1) not in best_ms:
+                continue
+            self.pw_stack = {i: cand}
+            self._plans.clear()
+            ops2, _cnt2 = self.build_plan(0, nb)
+            k = {li: kk for kk, (_kind, _name, _b, _f, li) in enumerate(self._plan_meta)}[i]
+            o = ops2[k]
+            t = {}
+            for rnd in range(2):
+                for v in [_lib.PW_TS] + ([_lib.PW_TS2] if cand["pair_ok"] else []):
+                    o.variant = v
+                    _lib.check(self.lib.yr_run_ops(C.byref(o), 1, st), "yr_run_ops")
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(reps):
+                        _lib.check(self.lib.yr_run_ops(C.byref(o), 1, st), "yr_run_ops")
+                    e1.record()
+                    torch.cuda.synchronize(self.device)
+                    t[v] = min(t.get(v, 1e9), e0.elapsed_time(e1) / reps)
+            best = min(t, key=lambda v: t[v])
+            sep = best_ms[i] + best_ms[i + 1]
+            keep = t[best] < 0.97 * sep
+            self.stack_log.append((self.net.layers[i].name, self.net.layers[i + 1].name, round(t[best] * 1e3, 1),
+                                   round(sep * 1e3, 1), keep))
+            if keep:
+                cand["variant"] = best
+            else:
+                stack_cands = {j: c for j, c in stack_cands.items() if j != i}
+        self.pw_stack = {i: c for i, c in stack_cands.items() if i in best_ms and (i + 1) in best_ms}
         self._plans.clear()  # plans were built with the provisional variants
 
     # ---- plan ---------------------------------------------------------------------
@@ -427,6 +507,24 @@ class Engine:
                                    + (L.k * L.k + 2) * x.Clog + x.Clog * b.out.Clog + 2 * b.out.Clog)
                 meta.append(("dwpw", L.name + "+" + b.name.split("_")[-1], fused_bytes, L.flops + b.flops, i))
                 self._ref_bytes[meta[-1][1]] = L.bytes_alg + b.bytes_alg  # SURVEY 8d per-layer accounting of the two layers
+                skip = 1
+                continue
+            if i in self.pw_stack:
+                st_, b = self.pw_stack[i], self.net.layers[i + 1]
+                o.kind, o.act, o.variant = _lib.OP_PW, _ACT[b.act], st_["variant"]
+                o.B, o.H, o.W, o.C = nb, x.H, x.W, x.C
+                o.Ho, o.Wo, o.N = L.out.H, L.out.W, int(st_["w"].shape[1])
+                o.k, o.stride = 1, 1
+                o.ld_in, o.ld_out, o.ld_in2 = x.buf.ld, L.out.buf.ld, b.out.buf.ld
+                o.K2, o.K3 = st_["n1"], st_["first_linear"]
+                o.in_, o.out, o.aux = _ptr(x, chunk0, slot), _ptr(L.out, chunk0), _ptr(b.out, chunk0)
+                o.w, o.bias, o.w_tc = st_["w"].data_ptr(), st_["bias"].data_ptr(), st_["img"].data_ptr()
+                if L.gate is not None:
+                    o.scale = gate_ptr[id(L.gate)]
+                shared = 4 * x.H * x.W * x.Clog   # the input both convs read: counted once
+                name = L.name + " | " + b.name.split("*")[-1]
+                meta.append(("pw", name, L.bytes_alg + b.bytes_alg - shared, L.flops + b.flops, i))
+                self._ref_bytes[name] = L.bytes_alg + b.bytes_alg
                 skip = 1
                 continue
             meta.append((L.kind, L.name, L.bytes_alg, L.flops, i))
