@@ -449,7 +449,10 @@ def run_b200(a):
         "verified": verified, "verify": verify_report, "multi_gpu_equivalence": equivalence,
         "pw_kernel_picks": {"tc": sum(1 for v in picks.values() if v == "tc"), "ts": sum(1 for v in picks.values() if v == "ts"),
                             "ts2_cta_pair": sum(1 for v in picks.values() if v == "ts2"),
-                            "per_layer": picks},
+                            "per_layer": picks,
+                            # pairs of 1x1 convs reading the same tensor, run as one GEMM with two destinations:
+                            # (first, second, stacked us, separate us, kept) as the autotuner measured them
+                            "stacked_pairs": [list(t) for t in getattr(eng, "stack_log", [])]},
     }
 
     if rank == 0 and not a.no_roofline:
