@@ -83,6 +83,27 @@ def test_fused_depthwise_pointwise_equals_separate(built_lib, anchors, name, hw,
     assert mf.engine.build_plan(0, B)[1] == mu.engine.build_plan(0, B)[1] - len(mf.engine.dwpw_blob)
 
 
+@pytest.mark.parametrize("autotune", [False, True])
+@pytest.mark.parametrize("name,hw,B", [("mobilenetv2x75", (128, 160), 3), ("efficientnetlite0", (96, 128), 2)])
+def test_stacked_pointwise_equals_separate(built_lib, anchors, name, hw, B, autotune):
+    """Engine with the stacked two-destination GEMMs (a head stage's y conv + the next bottom-up conv, which read the
+    same gated tensor after the folding) == engine running them as two ops, bit for bit; without the autotuner every
+    candidate pair is stacked (two launches less), with it a pair may be left alone if it measured slower."""
+    ncls = 80
+    nd = NetDef(name, ncls, hw)
+    w = synthetic_weights(nd.weight_shapes, ncls, seed=43)
+    x = torch.rand(B, hw[0], hw[1], 3, generator=torch.Generator().manual_seed(8)).cuda()
+    ms = yolov3_body((B, hw[0], hw[1], 3), name, 3, num_classes=ncls, stack_pw=True, autotune=autotune).set_weights(w, anchors)
+    mu = yolov3_body((B, hw[0], hw[1], 3), name, 3, num_classes=ncls, stack_pw=False, autotune=autotune).set_weights(w, anchors)
+    assert len(mu.engine.pw_stack) == 0
+    if not autotune:
+        assert len(ms.engine.pw_stack) == 2
+    ys, yu = ms(x), mu(x)
+    for a, b in zip(ys, yu):
+        assert torch.equal(a, b), float((a - b).abs().max())
+    assert ms.engine.build_plan(0, B)[1] == mu.engine.build_plan(0, B)[1] - len(ms.engine.pw_stack)
+
+
 @pytest.mark.parametrize("name,hw,B", [("mobilenetv2x75", (128, 160), 3), ("efficientnetb3", (64, 96), 2),
                                        ("efficientnetlite0", (96, 128), 2)])
 def test_folded_linear_convs_match_unfolded(built_lib, anchors, name, hw, B):

@@ -104,7 +104,7 @@ class YOLO(object):
         def model_body(inputs, **kw):
             return yolov3_body(inputs, model_name=backbone_name, drop_rate=0.2, data_format="channels_last", **kw)
 
-        extra = {k: FLAGS[k] for k in ('micro_batch', 'device', 'pw_variant', 'fuse_se', 'lanes', 'autotune', 'fuse_up2', 'fuse_dwpw', 'fold_linear') if k in FLAGS}
+        extra = {k: FLAGS[k] for k in ('micro_batch', 'device', 'pw_variant', 'fuse_se', 'lanes', 'autotune', 'fuse_up2', 'fuse_dwpw', 'fold_linear', 'stack_pw') if k in FLAGS}
         self.yolo_model = YoloModel(model_body, num_anchors, self.num_scales, self.class_names, model_path,
                                     self.anchors, self.input_shape, self.score, self.nms, self.with_classes,
                                     batch=batch, weights=weights, input_u8=bool(FLAGS.get('input_u8', False)),

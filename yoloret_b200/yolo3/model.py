@@ -34,11 +34,13 @@ class YoloBody:
     ``load_weights`` / ``set_weights`` (reference: an ``AdvLossModel``, model.py:342)."""
 
     def __init__(self, input_shape, model_name, num_anchors, num_classes, micro_batch=None, device=None,
-                 pw_variant=_lib.PW_AUTO, input_u8=False, num_scales=3, fuse_se=True, lanes=1, autotune=True, fuse_up2=True, fuse_dwpw=True, fold_linear=True):
+                 pw_variant=_lib.PW_AUTO, input_u8=False, num_scales=3, fuse_se=True, lanes=1, autotune=True, fuse_up2=True, fuse_dwpw=True, fold_linear=True,
+                 stack_pw=True):
         self.batch, self.input_hw = int(input_shape[0]), (int(input_shape[1]), int(input_shape[2]))
         self.model_name, self.num_anchors, self.num_classes = model_name, num_anchors, num_classes
         self._kw = dict(micro_batch=micro_batch, device=device, pw_variant=pw_variant, input_u8=input_u8,
-                        num_scales=num_scales, fuse_se=fuse_se, lanes=lanes, autotune=autotune, fuse_up2=fuse_up2, fuse_dwpw=fuse_dwpw, fold_linear=fold_linear)
+                        num_scales=num_scales, fuse_se=fuse_se, lanes=lanes, autotune=autotune, fuse_up2=fuse_up2, fuse_dwpw=fuse_dwpw, fold_linear=fold_linear,
+                        stack_pw=stack_pw)
         self.engine: Optional[Engine] = None
         from ..netdef import NetDef
         self.netdef = NetDef(model_name, num_classes, self.input_hw, num_anchors)
@@ -85,7 +87,7 @@ def yolov3_body(inputs, model_name, num_anchors, **kwargs):
     kwargs = dict(kwargs)
     kwargs.pop("drop_rate", None)
     eng = {k: kwargs.pop(k) for k in ("micro_batch", "device", "pw_variant", "input_u8", "num_scales", "fuse_se",
-                                      "lanes", "autotune", "fuse_up2", "fuse_dwpw", "fold_linear") if k in kwargs}
+                                      "lanes", "autotune", "fuse_up2", "fuse_dwpw", "fold_linear", "stack_pw") if k in kwargs}
     for k in kwargs:
         if k not in _GLOBAL_PARAM_FIELDS:  # namedtuple._replace raises ValueError in the reference
             raise ValueError("Got unexpected field names: %r" % [k])
